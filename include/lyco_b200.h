@@ -1,0 +1,159 @@
+/*
+ * lyco_b200.h — C ABI of the B200-native LyCORIS adapter-layer engine.
+ *
+ * Drop-in boundary for ONE hot path of KohakuBlueleaf/LyCORIS: the per-layer
+ * delta-weight application (LoCon / LoHa / LoKr / (IA)^3 / DyLoRA) on a wrapped
+ * nn.Linear / nn.Conv2d, forward + backward.  The reference has no FFI for this
+ * path (it is 100 % PyTorch eager); each entry point below names the reference
+ * Python call sites whose ATen launches it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; the text of the
+ *     last failure on the calling thread is returned by lyco_last_error();
+ *   - pointers are raw CUDA device pointers owned by the caller; no tensor
+ *     ownership crosses the boundary; the library never allocates device memory
+ *     that outlives a call;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, no
+ *     host synchronisation happens inside any call (CUDA-graph capturable);
+ *   - matrices are row-major; "ld" arguments are leading dimensions in ELEMENTS;
+ *   - there is NO CPU implementation behind this ABI: calls fail when the device
+ *     is not sm_100.
+ */
+#ifndef LYCO_B200_H_
+#define LYCO_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LYCO_ABI_VERSION 1
+
+/* element types */
+enum { LYCO_BF16 = 0, LYCO_F16 = 1, LYCO_F32 = 2 };
+
+/* adapter algorithms — lycoris/wrapper.py:45-55 network_module_dict keys */
+enum {
+  LYCO_ALGO_LOCON = 0, /* lycoris/modules/locon.py  */
+  LYCO_ALGO_LOHA = 1,  /* lycoris/modules/loha.py   */
+  LYCO_ALGO_LOKR = 2,  /* lycoris/modules/lokr.py   */
+  LYCO_ALGO_IA3 = 3,   /* lycoris/modules/ia3.py    */
+  LYCO_ALGO_DYLORA = 4 /* lycoris/modules/dylora.py (uses the LOCON kernels) */
+};
+
+/* ------------------------------------------------------------------------- */
+/* library / device                                                           */
+/* ------------------------------------------------------------------------- */
+
+int lyco_abi_version(void);
+/* thread-local text of the last error (never NULL) */
+const char* lyco_last_error(void);
+/* 0 when `device` is a compute-capability-10.x part the kernels can run on */
+int lyco_device_check(int device);
+/* number of kernels this library has launched since load (bench gpu_launches) */
+uint64_t lyco_launch_count(void);
+
+/* ------------------------------------------------------------------------- */
+/* dense contraction (tcgen05 + TMA)                                          */
+/* ------------------------------------------------------------------------- */
+
+/*
+ * C[M,N] (+)= A · Bᵀ (+ bias), bf16 (or fp16) operands, fp32 accumulation in TMEM.
+ *
+ *   A is the [M x K] operand, B the [N x K] operand (K = reduction length).
+ *   a_mn_major = 0: A stored row-major [M, K]  (reduction index contiguous)
+ *   a_mn_major = 1: A stored row-major [K, M]  (output-row index contiguous)
+ *   likewise b_mn_major for B ([N, K] or [K, N]).
+ *   lda / ldb: leading dimension (elements) of the array as stored.
+ *   c_dtype: LYCO_BF16 / LYCO_F16 (store, optional bias[N]) or LYCO_F32
+ *            (store; with split_k > 1 partials are reduced with fp32 atomics
+ *             into C, which the call zero-fills first).
+ *   ab_dtype: LYCO_BF16 or LYCO_F16.
+ *   bias / bias_dtype: optional [N] vector added in the epilogue (NULL = none).
+ *   split_k: 0 = choose automatically; otherwise number of reduction splits.
+ *
+ * Replaces, per wrapped layer and step, the ATen library calls at
+ *   forward   base + delta contraction  lycoris/modules/locon.py:317,331
+ *                                        (same in loha.py:309,321 lokr.py:551,565
+ *                                         ia3.py:136,143 dylora.py:150,156)
+ *   backward  dX (both branches) and dδ = dYᵀ·X produced by autograd for those.
+ * Alignment: base pointers 16-byte aligned, lda/ldb/ldc multiples of 8.
+ */
+int lyco_gemm(const void* A, int a_mn_major, int64_t lda,
+              const void* B, int b_mn_major, int64_t ldb,
+              void* C, int c_dtype, int64_t ldc,
+              const void* bias, int bias_dtype,
+              int M, int N, int K,
+              int ab_dtype, int split_k, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* weight-side kernels (HBM-bound)                                            */
+/* ------------------------------------------------------------------------- */
+
+/*
+ * Describes ΔW of one adapter on one layer.  Weights are handled as row-major
+ * [out_dim, in_dim] with in_dim = in_channels*kh*kw for convolutions (the
+ * reference flattens the same way: locon.py:207, loha.py:76, lokr.py:131-135).
+ *
+ * Rounding chain (reproduces the reference's rounding points):
+ *   raw   = factor product in fp32
+ *   raw   = rnd_pre(raw)                      if pre_round (product dtype = 16-bit)
+ *   d     = rnd_pre(raw * m_pre)
+ *   d     = rnd_w(d)                          cast to the base-weight dtype
+ *   d     = rnd_w(d * m_post1); d = rnd_w(d * m_post2)
+ *   W'    = rnd_w(W + d)
+ * rnd_pre rounds to `pre_dtype` when pre_round != 0, rnd_w rounds to w_dtype.
+ */
+typedef struct lyco_delta_desc {
+  int32_t algo;      /* LYCO_ALGO_*                                          */
+  int32_t out_dim;   /* N                                                     */
+  int32_t in_dim;    /* K' = in_channels * kh * kw                            */
+  int32_t rank;      /* r  (LOCON/LOHA/DYLORA)                                */
+  int32_t up, uq;    /* LOKR: w1 is [up, uq]   (lokr.py:161-163)              */
+  int32_t vp, vq;    /* LOKR: w2 is [vp, vq]   (vq includes kh*kw)            */
+  int32_t on_input;  /* IA3: scale input channels (ia3.py:92-97)              */
+  int32_t ia3_group; /* IA3 on_input: elements per input channel (kh*kw)      */
+  int32_t f_dtype;   /* dtype of the factor arrays (LYCO_BF16/F16/F32)        */
+  int32_t w_dtype;   /* dtype of W and W' (LYCO_BF16/F16)                     */
+  int32_t pre_round; /* see rounding chain                                    */
+  int32_t pre_dtype; /* dtype rnd_pre rounds to                               */
+  float m_in;        /* DYLORA: multiplier folded into `down` (dylora.py:117) */
+  float m_pre, m_post1, m_post2;
+  /* factor arrays:
+   *   LOCON/DYLORA f0 = up   [N, r]        f1 = down [r, K']
+   *   LOHA         f0 = w1a  [N, r]        f1 = w1b  [r, K']
+   *                f2 = w2a  [N, r]        f3 = w2b  [r, K']
+   *   LOKR         f0 = w1   [up, uq]      f1 = w2   [vp, vq]
+   *   IA3          f0 = w    [N] or [K'/ia3_group]                            */
+  const void* f0;
+  const void* f1;
+  const void* f2;
+  const void* f3;
+} lyco_delta_desc_t;
+
+/*
+ * W_out[N,K'] = W + ΔW  (rounded as described above).  One pass over W.
+ * Replaces make_weight/get_weight + `.to(dtype)*scale` + `W + ΔW*mult`
+ *   lycoris/modules/locon.py:198-219,321-328   loha.py:194-226,310-318
+ *   lycoris/modules/lokr.py:358-381,552-562 (+ functional/lokr.py:11-20 kron)
+ *   lycoris/modules/ia3.py:91-102,137-141      dylora.py:97-117,295-298
+ * and removes `delta_weight = new_weight - base_weight` (locon.py:330 …).
+ */
+int lyco_merge_weight(const lyco_delta_desc_t* d, const void* W, void* W_out,
+                      void* stream);
+
+/*
+ * Factor gradients from dW' (fp32 [N,K'], = dYᵀ·X of the merged contraction).
+ * g0..g3 receive fp32 gradients with the shapes of f0..f3 (unused ones NULL);
+ * they are zero-filled by the call.  `W` is needed by IA3 only.
+ * Replaces autograd through the chain listed at lyco_merge_weight, incl.
+ * HadaWeight.backward lycoris/functional/loha.py:18-30 and torch.kron backward.
+ */
+int lyco_factor_grads(const lyco_delta_desc_t* d, const float* dW, const void* W,
+                      float* g0, float* g1, float* g2, float* g3, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LYCO_B200_H_ */

@@ -1,0 +1,377 @@
+// C-ABI entry points (include/lyco_b200.h) and the host-side launch logic.
+// No torch types cross this boundary; nothing here synchronises the host with the device.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "../../include/lyco_b200.h"
+#include "gemm_sm100.cuh"
+#include "weight_kernels.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+
+#define LYCO_CUDA(expr)                                                                  \
+  do {                                                                                   \
+    cudaError_t e__ = (expr);                                                            \
+    if (e__ != cudaSuccess) return fail("%s failed: %s", #expr, cudaGetErrorString(e__)); \
+  } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+struct DeviceInfo {
+  int device = -1;
+  int sms = 0;
+  int cc_major = 0;
+};
+// per-device cache; the current device is queried on every call (cheap) so that multi-GPU
+// processes and device switches stay correct
+int device_info(DeviceInfo* out) {
+  static DeviceInfo cache[64];
+  int dev = 0;
+  LYCO_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail("device index %d out of range", dev);
+  if (cache[dev].device != dev) {
+    DeviceInfo d;
+    d.device = dev;
+    LYCO_CUDA(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
+    LYCO_CUDA(cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+    cache[dev] = d;
+  }
+  *out = cache[dev];
+  if (out->cc_major != 10)
+    return fail("lycoris_b200 kernels need compute capability 10.x (B200); device %d is %d.x", dev,
+                out->cc_major);
+  return 0;
+}
+
+// 2-D tiled tensor map over a row-major [outer, inner] array of 16-bit elements, 128B swizzle
+int make_tmap(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
+              uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return fail("cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstr[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail("cuTensorMapEncodeTiled failed (%d): base=%p inner=%llu outer=%llu ld=%llu box=%ux%u",
+                static_cast<int>(r), base, (unsigned long long)inner, (unsigned long long)outer,
+                (unsigned long long)ld_elems, box_inner, box_outer);
+  return 0;
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const lyco::GemmParams& p, int grid,
+                cudaStream_t stream) {
+  auto kern = lyco::gemm_sm100_kernel<BN, A_MN, B_MN, EPI>;
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!configured[dev & 63]) {
+    LYCO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   lyco::GemmCfg<BN>::SMEM_BYTES));
+    configured[dev & 63] = true;
+  }
+  kern<<<grid, lyco::GEMM_THREADS, lyco::GemmCfg<BN>::SMEM_BYTES, stream>>>(ta, tb, p);
+  LYCO_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+template <int BN>
+int dispatch_gemm(bool a_mn, bool b_mn, int epi, const CUtensorMap& ta, const CUtensorMap& tb,
+                  const lyco::GemmParams& p, int grid, cudaStream_t s) {
+  using namespace lyco;
+  if (!a_mn && !b_mn) {
+    if (epi == EPI_STORE16) return launch_gemm<BN, false, false, EPI_STORE16>(ta, tb, p, grid, s);
+    if (epi == EPI_STORE_F32) return launch_gemm<BN, false, false, EPI_STORE_F32>(ta, tb, p, grid, s);
+    return launch_gemm<BN, false, false, EPI_ATOMIC_F32>(ta, tb, p, grid, s);
+  }
+  if (!a_mn && b_mn) {
+    if (epi == EPI_STORE16) return launch_gemm<BN, false, true, EPI_STORE16>(ta, tb, p, grid, s);
+    if (epi == EPI_STORE_F32) return launch_gemm<BN, false, true, EPI_STORE_F32>(ta, tb, p, grid, s);
+    return launch_gemm<BN, false, true, EPI_ATOMIC_F32>(ta, tb, p, grid, s);
+  }
+  if (a_mn && b_mn) {
+    if (epi == EPI_STORE16) return launch_gemm<BN, true, true, EPI_STORE16>(ta, tb, p, grid, s);
+    if (epi == EPI_STORE_F32) return launch_gemm<BN, true, true, EPI_STORE_F32>(ta, tb, p, grid, s);
+    return launch_gemm<BN, true, true, EPI_ATOMIC_F32>(ta, tb, p, grid, s);
+  }
+  if (epi == EPI_STORE16) return launch_gemm<BN, true, false, EPI_STORE16>(ta, tb, p, grid, s);
+  if (epi == EPI_STORE_F32) return launch_gemm<BN, true, false, EPI_STORE_F32>(ta, tb, p, grid, s);
+  return launch_gemm<BN, true, false, EPI_ATOMIC_F32>(ta, tb, p, grid, s);
+}
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// Relative cost of one 128 x bn tile step: tensor-pipe time ~ bn, L2->SM feed ~ (128 + bn).
+inline double tile_cost(int bn) {
+  const double mma = bn, feed = 0.85 * (128 + bn);
+  return mma > feed ? mma : feed;
+}
+
+int pick_block_n(int M, int N, int sms, int splits_hint) {
+  int best = 64;
+  double best_cost = 1e30;
+  const int cands[3] = {256, 128, 64};
+  for (int bn : cands) {
+    const long tiles = static_cast<long>(cdiv(M, 128)) * cdiv(N, bn) * (splits_hint > 0 ? splits_hint : 1);
+    const long waves = (tiles + sms - 1) / sms;
+    const double cost = waves * tile_cost(bn);
+    if (cost < best_cost * 0.999) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+int pick_splits(long tiles, int k_blocks, int sms) {
+  int best = 1;
+  double best_cost = 1e30;
+  const int smax = k_blocks / 4 > 0 ? (k_blocks / 4 < 64 ? k_blocks / 4 : 64) : 1;
+  for (int s = 1; s <= smax; ++s) {
+    const long units = tiles * s;
+    const long waves = (units + sms - 1) / sms;
+    // time ~ waves * (k per unit) + epilogue/atomic overhead per unit
+    const double cost = waves * (static_cast<double>(k_blocks) / s + 6.0) + 0.5 * s;
+    if (cost < best_cost * 0.98) { best_cost = cost; best = s; }
+  }
+  return best;
+}
+
+int check_desc(const lyco_delta_desc_t* d) {
+  if (!d) return fail("null delta descriptor");
+  if (d->out_dim <= 0 || d->in_dim <= 0) return fail("bad weight shape %d x %d", d->out_dim, d->in_dim);
+  if (d->w_dtype != LYCO_BF16 && d->w_dtype != LYCO_F16)
+    return fail("weight dtype must be bf16 or f16 (got %d)", d->w_dtype);
+  switch (d->algo) {
+    case LYCO_ALGO_LOCON:
+    case LYCO_ALGO_DYLORA:
+      if (d->rank <= 0 || !d->f0 || !d->f1) return fail("locon/dylora need rank>0 and f0,f1");
+      break;
+    case LYCO_ALGO_LOHA:
+      if (d->rank <= 0 || !d->f0 || !d->f1 || !d->f2 || !d->f3) return fail("loha needs rank>0 and f0..f3");
+      break;
+    case LYCO_ALGO_LOKR:
+      if (!d->f0 || !d->f1 || d->up <= 0 || d->uq <= 0 || d->vp <= 0 || d->vq <= 0)
+        return fail("lokr needs f0,f1 and positive up,uq,vp,vq");
+      if (static_cast<int64_t>(d->up) * d->vp != d->out_dim || static_cast<int64_t>(d->uq) * d->vq != d->in_dim)
+        return fail("lokr factor shapes (%d,%d)x(%d,%d) do not tile %d x %d", d->up, d->uq, d->vp, d->vq,
+                    d->out_dim, d->in_dim);
+      break;
+    case LYCO_ALGO_IA3:
+      if (!d->f0) return fail("ia3 needs f0");
+      if (d->on_input && (d->ia3_group <= 0 || d->in_dim % d->ia3_group))
+        return fail("ia3 on_input: bad group %d for in_dim %d", d->ia3_group, d->in_dim);
+      break;
+    default:
+      return fail("unknown algo %d", d->algo);
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lyco_abi_version(void) { return LYCO_ABI_VERSION; }
+const char* lyco_last_error(void) { return g_err; }
+uint64_t lyco_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int lyco_device_check(int device) {
+  int n = 0;
+  LYCO_CUDA(cudaGetDeviceCount(&n));
+  if (device < 0 || device >= n) return fail("no CUDA device %d (count %d)", device, n);
+  int major = 0;
+  LYCO_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  if (major != 10) return fail("device %d has compute capability %d.x, need 10.x (B200)", device, major);
+  return 0;
+}
+
+int lyco_gemm(const void* A, int a_mn_major, int64_t lda, const void* B, int b_mn_major, int64_t ldb,
+              void* C, int c_dtype, int64_t ldc, const void* bias, int bias_dtype, int M, int N, int K,
+              int ab_dtype, int split_k, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (M <= 0 || N <= 0 || K <= 0) return fail("lyco_gemm: empty problem %d x %d x %d", M, N, K);
+  if (!A || !B || !C) return fail("lyco_gemm: null operand");
+  if (ab_dtype != LYCO_BF16 && ab_dtype != LYCO_F16) return fail("lyco_gemm: operands must be bf16/f16");
+  if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C)) & 15)
+    return fail("lyco_gemm: operand base pointers must be 16-byte aligned");
+  if ((lda | ldb | ldc) & 7) return fail("lyco_gemm: lda/ldb/ldc must be multiples of 8 (got %lld %lld %lld)",
+                                          (long long)lda, (long long)ldb, (long long)ldc);
+  if (c_dtype != LYCO_F32 && c_dtype != ab_dtype) return fail("lyco_gemm: C must be f32 or the operand dtype");
+  if (bias && c_dtype == LYCO_F32) return fail("lyco_gemm: bias only with 16-bit output");
+  DeviceInfo di;
+  if (device_info(&di)) return 1;
+
+  const int k_blocks = cdiv(K, lyco::GEMM_BLOCK_K);
+  int splits = 1;
+  const int m_tiles = cdiv(M, lyco::GEMM_BLOCK_M);
+  int bn = pick_block_n(M, N, di.sms, 1);
+  if (c_dtype == LYCO_F32) {
+    // wgrad-like: few output tiles, long reduction -> split the reduction across CTAs
+    bn = N >= 256 ? 256 : (N >= 128 ? 128 : 64);
+    const long tiles = static_cast<long>(m_tiles) * cdiv(N, bn);
+    splits = split_k > 0 ? split_k : pick_splits(tiles, k_blocks, di.sms);
+    if (splits > k_blocks) splits = k_blocks;
+  }
+  const int n_tiles = cdiv(N, bn);
+
+  CUtensorMap ta, tb;
+  if (!a_mn_major) { if (make_tmap(&ta, A, K, M, lda, 64, 128)) return 1; }
+  else             { if (make_tmap(&ta, A, M, K, lda, 64, 64)) return 1; }
+  if (!b_mn_major) { if (make_tmap(&tb, B, K, N, ldb, 64, bn)) return 1; }
+  else             { if (make_tmap(&tb, B, N, K, ldb, 64, 64)) return 1; }
+
+  lyco::GemmParams p;
+  p.C = C; p.bias = bias; p.ldc = ldc; p.M = M; p.N = N; p.K = K;
+  p.m_tiles = m_tiles; p.n_tiles = n_tiles; p.splits = splits; p.k_blocks = k_blocks;
+  p.fmt = (ab_dtype == LYCO_BF16) ? 1 : 0;
+  p.bias_dtype = bias_dtype;
+
+  int epi = lyco::EPI_STORE16;
+  if (c_dtype == LYCO_F32) {
+    epi = splits > 1 ? lyco::EPI_ATOMIC_F32 : lyco::EPI_STORE_F32;
+    if (splits > 1) {
+      if (ldc == N) LYCO_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * static_cast<size_t>(M) * N, stream));
+      else LYCO_CUDA(cudaMemset2DAsync(C, ldc * sizeof(float), 0, N * sizeof(float), M, stream));
+    }
+  }
+  const long total = static_cast<long>(m_tiles) * n_tiles * splits;
+  const int grid = static_cast<int>(total < di.sms ? total : di.sms);
+  const bool a_mn = a_mn_major != 0, b_mn = b_mn_major != 0;
+  if (bn == 256) return dispatch_gemm<256>(a_mn, b_mn, epi, ta, tb, p, grid, stream);
+  if (bn == 128) return dispatch_gemm<128>(a_mn, b_mn, epi, ta, tb, p, grid, stream);
+  return dispatch_gemm<64>(a_mn, b_mn, epi, ta, tb, p, grid, stream);
+}
+
+int lyco_merge_weight(const lyco_delta_desc_t* d, const void* W, void* W_out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (check_desc(d)) return 1;
+  if (!W || !W_out) return fail("lyco_merge_weight: null weight pointer");
+  DeviceInfo di;
+  if (device_info(&di)) return 1;
+  const uint16_t* w = static_cast<const uint16_t*>(W);
+  uint16_t* wo = static_cast<uint16_t*>(W_out);
+  const int64_t total = static_cast<int64_t>(d->out_dim) * d->in_dim;
+  const bool aligned16 = ((reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(W_out)) & 15) == 0;
+  switch (d->algo) {
+    case LYCO_ALGO_LOCON:
+    case LYCO_ALGO_DYLORA:
+    case LYCO_ALGO_LOHA: {
+      if (!aligned16) return fail("lyco_merge_weight: W / W_out must be 16-byte aligned");
+      const int grid = cdiv(d->out_dim, lyco::LR_ROWS) * cdiv(d->in_dim, lyco::LR_COLS);
+      if (d->algo == LYCO_ALGO_LOHA) lyco::merge_lowrank_kernel<true><<<grid, 256, 0, stream>>>(*d, w, wo);
+      else lyco::merge_lowrank_kernel<false><<<grid, 256, 0, stream>>>(*d, w, wo);
+      break;
+    }
+    case LYCO_ALGO_LOKR: {
+      const bool vec = aligned16 && (d->vq % 8 == 0);
+      const int64_t work = vec ? total / 8 : total;
+      int grid = static_cast<int>((work + 255) / 256);
+      const int cap = di.sms * 16;
+      if (grid > cap) grid = cap;
+      if (vec) lyco::merge_lokr_kernel<8><<<grid, 256, 0, stream>>>(*d, w, wo);
+      else lyco::merge_lokr_kernel<1><<<grid, 256, 0, stream>>>(*d, w, wo);
+      break;
+    }
+    case LYCO_ALGO_IA3: {
+      int grid = static_cast<int>((total + 255) / 256);
+      const int cap = di.sms * 16;
+      if (grid > cap) grid = cap;
+      lyco::merge_ia3_kernel<<<grid, 256, 0, stream>>>(*d, w, wo);
+      break;
+    }
+  }
+  LYCO_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+int lyco_factor_grads(const lyco_delta_desc_t* d, const float* dW, const void* W, float* g0, float* g1,
+                      float* g2, float* g3, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (check_desc(d)) return 1;
+  if (!dW) return fail("lyco_factor_grads: null dW");
+  DeviceInfo di;
+  if (device_info(&di)) return 1;
+  const int N = d->out_dim, K = d->in_dim, r = d->rank;
+  switch (d->algo) {
+    case LYCO_ALGO_LOCON:
+    case LYCO_ALGO_DYLORA:
+    case LYCO_ALGO_LOHA: {
+      const bool loha = d->algo == LYCO_ALGO_LOHA;
+      if (!g0 || !g1 || (loha && (!g2 || !g3))) return fail("lyco_factor_grads: missing gradient buffers");
+      LYCO_CUDA(cudaMemsetAsync(g0, 0, sizeof(float) * static_cast<size_t>(N) * r, stream));
+      LYCO_CUDA(cudaMemsetAsync(g1, 0, sizeof(float) * static_cast<size_t>(r) * K, stream));
+      if (loha) {
+        LYCO_CUDA(cudaMemsetAsync(g2, 0, sizeof(float) * static_cast<size_t>(N) * r, stream));
+        LYCO_CUDA(cudaMemsetAsync(g3, 0, sizeof(float) * static_cast<size_t>(r) * K, stream));
+      }
+      const int grid = cdiv(N, lyco::LR_ROWS) * cdiv(K, lyco::LR_COLS);
+      if (loha) lyco::grad_lowrank_kernel<true><<<grid, 256, 0, stream>>>(*d, dW, g0, g1, g2, g3);
+      else lyco::grad_lowrank_kernel<false><<<grid, 256, 0, stream>>>(*d, dW, g0, g1, g2, g3);
+      break;
+    }
+    case LYCO_ALGO_LOKR: {
+      if (!g0 || !g1) return fail("lyco_factor_grads: missing gradient buffers");
+      const size_t n_w1 = static_cast<size_t>(d->up) * d->uq;
+      LYCO_CUDA(cudaMemsetAsync(g0, 0, sizeof(float) * n_w1, stream));
+      const int64_t plane = static_cast<int64_t>(d->vp) * d->vq;
+      const int grid = static_cast<int>((plane + 255) / 256);
+      if (n_w1 * sizeof(float) <= 32 * 1024)
+        lyco::grad_lokr_kernel<true><<<grid, 256, n_w1 * sizeof(float), stream>>>(*d, dW, g0, g1);
+      else
+        lyco::grad_lokr_kernel<false><<<grid, 256, 0, stream>>>(*d, dW, g0, g1);
+      break;
+    }
+    case LYCO_ALGO_IA3: {
+      if (!g0 || !W) return fail("lyco_factor_grads: ia3 needs g0 and W");
+      const uint16_t* w = static_cast<const uint16_t*>(W);
+      if (!d->on_input) {
+        lyco::grad_ia3_kernel<<<cdiv(N, 8), 256, 0, stream>>>(*d, dW, w, g0);
+      } else {
+        LYCO_CUDA(cudaMemsetAsync(g0, 0, sizeof(float) * static_cast<size_t>(K / d->ia3_group), stream));
+        dim3 grid(cdiv(K, 256), cdiv(N, 64));
+        lyco::grad_ia3_kernel<<<grid, 256, 0, stream>>>(*d, dW, w, g0);
+      }
+      break;
+    }
+  }
+  LYCO_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+}  // extern "C"

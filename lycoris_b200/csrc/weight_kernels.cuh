@@ -1,0 +1,404 @@
+// Weight-side (HBM-bound) kernels: merged-weight assembly W' = W + dW(factors) and the
+// factor gradients from dW' = dY^T X.  One pass over the [N, K'] weight each; factors are tiny
+// and live in shared memory / L1.  Element (n, k) of a convolution weight is addressed with
+// k = c*kh*kw + i*kw + j, exactly how the reference flattens it.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+#include "../../include/lyco_b200.h"
+
+namespace lyco {
+
+// ------------------------------------------------------------------ helpers --
+__device__ __forceinline__ float rnd(float x, int dtype) {
+  if (dtype == LYCO_BF16) return __bfloat162float(__float2bfloat16_rn(x));
+  if (dtype == LYCO_F16) return __half2float(__float2half_rn(x));
+  return x;
+}
+__device__ __forceinline__ float ld_f(const void* p, int dtype, int64_t i) {
+  if (dtype == LYCO_F32) return __ldg(reinterpret_cast<const float*>(p) + i);
+  if (dtype == LYCO_BF16)
+    return __bfloat162float(__ldg(reinterpret_cast<const __nv_bfloat16*>(p) + i));
+  return __half2float(__ldg(reinterpret_cast<const __half*>(p) + i));
+}
+__device__ __forceinline__ float cvt16(uint16_t h, int dtype) {
+  if (dtype == LYCO_BF16) return __uint_as_float(static_cast<uint32_t>(h) << 16);
+  return __half2float(*reinterpret_cast<const __half*>(&h));
+}
+__device__ __forceinline__ uint16_t to16(float x, int dtype) {
+  if (dtype == LYCO_BF16) {
+    __nv_bfloat16 v = __float2bfloat16_rn(x);
+    return *reinterpret_cast<uint16_t*>(&v);
+  }
+  __half v = __float2half_rn(x);
+  return *reinterpret_cast<uint16_t*>(&v);
+}
+
+struct Chain {
+  int pre_round, pre_dtype, w_dtype;
+  float m_pre, m_post1, m_post2;
+};
+// raw factor product -> delta on the weight's grid (the reference's rounding points)
+__device__ __forceinline__ float apply_chain(float raw, const Chain& c) {
+  const int pd = c.pre_round ? c.pre_dtype : LYCO_F32;
+  float d = rnd(raw, pd);
+  d = rnd(d * c.m_pre, pd);
+  d = rnd(d, c.w_dtype);
+  d = rnd(d * c.m_post1, c.w_dtype);
+  d = rnd(d * c.m_post2, c.w_dtype);
+  return d;
+}
+__device__ __forceinline__ float merged(float w, float delta, int w_dtype) {
+  return rnd(w + delta, w_dtype);
+}
+
+// Tile geometry shared by the low-rank (LoCon / DyLoRA / LoHa) kernels:
+//   256 threads, tile = 32 rows x 256 columns; warp w owns rows 4w..4w+3, lane l owns the
+//   8 consecutive columns 8l..8l+7 (one 16-byte vector of 16-bit weights).
+constexpr int LR_ROWS = 32;
+constexpr int LR_COLS = 256;
+constexpr int LR_RC = 16;  // rank chunk held in shared memory
+
+// stage [rows x rc] of `a` ([N, r] row-major) and [rc x cols] of `b` ([r, K'] row-major)
+__device__ __forceinline__ void lr_stage_factors(const void* a, const void* b, int f_dtype, int N,
+                                                 int K, int r, int n0, int k0, int r0, int rc,
+                                                 float (*sa)[LR_RC], float (*sb)[LR_COLS],
+                                                 int round_dtype, float b_mul) {
+  for (int i = threadIdx.x; i < LR_ROWS * LR_RC; i += blockDim.x) {
+    const int row = i / LR_RC, q = i % LR_RC;
+    float v = 0.f;
+    if (n0 + row < N && q < rc) v = rnd(ld_f(a, f_dtype, static_cast<int64_t>(n0 + row) * r + r0 + q), round_dtype);
+    sa[row][q] = v;
+  }
+  for (int i = threadIdx.x; i < LR_RC * LR_COLS; i += blockDim.x) {
+    const int q = i / LR_COLS, col = i % LR_COLS;
+    float v = 0.f;
+    if (q < rc && k0 + col < K) {
+      v = ld_f(b, f_dtype, static_cast<int64_t>(r0 + q) * K + k0 + col);
+      if (b_mul != 1.f) v = rnd(v * b_mul, f_dtype);  // dylora: down * (alpha/(b+1) * mult) in param dtype
+      v = rnd(v, round_dtype);
+    }
+    sb[q][col] = v;
+  }
+}
+
+// acc[4][8] += sa[rows][rc] * sb[rc][cols] for this thread's 4x8 patch
+__device__ __forceinline__ void lr_accumulate(float (&acc)[4][8], const float (*sa)[LR_RC],
+                                              const float (*sb)[LR_COLS], int rc, int warp,
+                                              int lane) {
+  for (int q = 0; q < rc; ++q) {
+    const float4 b0 = *reinterpret_cast<const float4*>(&sb[q][8 * lane]);
+    const float4 b1 = *reinterpret_cast<const float4*>(&sb[q][8 * lane + 4]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float a = sa[4 * warp + i][q];
+      acc[i][0] = fmaf(a, b0.x, acc[i][0]);
+      acc[i][1] = fmaf(a, b0.y, acc[i][1]);
+      acc[i][2] = fmaf(a, b0.z, acc[i][2]);
+      acc[i][3] = fmaf(a, b0.w, acc[i][3]);
+      acc[i][4] = fmaf(a, b1.x, acc[i][4]);
+      acc[i][5] = fmaf(a, b1.y, acc[i][5]);
+      acc[i][6] = fmaf(a, b1.z, acc[i][6]);
+      acc[i][7] = fmaf(a, b1.w, acc[i][7]);
+    }
+  }
+}
+
+// full product P[4][8] = a[n,:] . b[:,k] over all rank chunks
+__device__ __forceinline__ void lr_product(float (&acc)[4][8], const void* a, const void* b,
+                                           int f_dtype, int N, int K, int r, int n0, int k0,
+                                           float (*sa)[LR_RC], float (*sb)[LR_COLS],
+                                           int round_dtype, float b_mul) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  for (int r0 = 0; r0 < r; r0 += LR_RC) {
+    const int rc = min(LR_RC, r - r0);
+    __syncthreads();
+    lr_stage_factors(a, b, f_dtype, N, K, r, n0, k0, r0, rc, sa, sb, round_dtype, b_mul);
+    __syncthreads();
+    lr_accumulate(acc, sa, sb, rc, warp, lane);
+  }
+}
+
+// ------------------------------------------------------------- merge kernels --
+// LoCon / DyLoRA (LOHA = false) and LoHa (LOHA = true)
+template <bool LOHA>
+__global__ void __launch_bounds__(256) merge_lowrank_kernel(lyco_delta_desc_t d, const uint16_t* __restrict__ W,
+                                                            uint16_t* __restrict__ Wout) {
+  __shared__ __align__(16) float sa[LR_ROWS][LR_RC];
+  __shared__ __align__(16) float sb[LR_RC][LR_COLS];
+  const int N = d.out_dim, K = d.in_dim, r = d.rank;
+  const int k_tiles = (K + LR_COLS - 1) / LR_COLS;
+  const int n0 = (blockIdx.x / k_tiles) * LR_ROWS;
+  const int k0 = (blockIdx.x % k_tiles) * LR_COLS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const Chain ch{d.pre_round, d.pre_dtype, d.w_dtype, d.m_pre, d.m_post1, d.m_post2};
+  const int fround = d.pre_round ? d.pre_dtype : LYCO_F32;  // operands as the 16-bit matmul sees them
+
+  float p1[4][8];
+  lr_product(p1, d.f0, d.f1, d.f_dtype, N, K, r, n0, k0, sa, sb, fround, d.m_in);
+  if (LOHA) {
+    float p2[4][8];
+    lr_product(p2, d.f2, d.f3, d.f_dtype, N, K, r, n0, k0, sa, sb, fround, 1.f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) p1[i][j] = rnd(p1[i][j], fround) * rnd(p2[i][j], fround);
+  }
+  const int kc = k0 + 8 * lane;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int n = n0 + 4 * warp + i;
+    if (n >= N || kc >= K) continue;
+    const int64_t off = static_cast<int64_t>(n) * K + kc;
+    if (kc + 8 <= K && (K % 8) == 0) {
+      const uint4 wv = __ldg(reinterpret_cast<const uint4*>(W + off));
+      const uint16_t* wh = reinterpret_cast<const uint16_t*>(&wv);
+      uint4 ov;
+      uint16_t* oh = reinterpret_cast<uint16_t*>(&ov);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        oh[j] = to16(merged(cvt16(wh[j], d.w_dtype), apply_chain(p1[i][j], ch), d.w_dtype), d.w_dtype);
+      *reinterpret_cast<uint4*>(Wout + off) = ov;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (kc + j < K)
+          Wout[off + j] = to16(merged(cvt16(W[off + j], d.w_dtype), apply_chain(p1[i][j], ch), d.w_dtype), d.w_dtype);
+    }
+  }
+}
+
+// LoKr: dW[pu*vp+pv, u*vq+v] = w1[pu,u] * w2[pv,v]   (functional/lokr.py:11-20 via torch.kron)
+template <int VEC>
+__global__ void __launch_bounds__(256) merge_lokr_kernel(lyco_delta_desc_t d, const uint16_t* __restrict__ W,
+                                                         uint16_t* __restrict__ Wout) {
+  const int K = d.in_dim;
+  const int64_t total = static_cast<int64_t>(d.out_dim) * K / VEC;
+  const Chain ch{d.pre_round, d.pre_dtype, d.w_dtype, d.m_pre, d.m_post1, d.m_post2};
+  const int fround = d.pre_round ? d.pre_dtype : LYCO_F32;
+  const int kv = K / VEC;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(idx / kv);
+    const int k = static_cast<int>(idx % kv) * VEC;
+    const int pu = n / d.vp, pv = n % d.vp;
+    const int u = k / d.vq, v = k % d.vq;  // VEC divides vq -> the vector stays inside one w1 block
+    const float a = rnd(ld_f(d.f0, d.f_dtype, pu * d.uq + u), fround);
+    const int64_t off = static_cast<int64_t>(n) * K + k;
+    if (VEC == 8) {
+      const uint4 wv = __ldg(reinterpret_cast<const uint4*>(W + off));
+      const uint16_t* wh = reinterpret_cast<const uint16_t*>(&wv);
+      uint4 ov;
+      uint16_t* oh = reinterpret_cast<uint16_t*>(&ov);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float b = rnd(ld_f(d.f1, d.f_dtype, static_cast<int64_t>(pv) * d.vq + v + j), fround);
+        oh[j] = to16(merged(cvt16(wh[j], d.w_dtype), apply_chain(a * b, ch), d.w_dtype), d.w_dtype);
+      }
+      *reinterpret_cast<uint4*>(Wout + off) = ov;
+    } else {
+      const float b = rnd(ld_f(d.f1, d.f_dtype, static_cast<int64_t>(pv) * d.vq + v), fround);
+      Wout[off] = to16(merged(cvt16(W[off], d.w_dtype), apply_chain(a * b, ch), d.w_dtype), d.w_dtype);
+    }
+  }
+}
+
+// (IA)^3: W' = W * (1 + w*mult) on output rows or input channels (ia3.py:91-102)
+__global__ void __launch_bounds__(256) merge_ia3_kernel(lyco_delta_desc_t d, const uint16_t* __restrict__ W,
+                                                        uint16_t* __restrict__ Wout) {
+  const int K = d.in_dim;
+  const int64_t total = static_cast<int64_t>(d.out_dim) * K;
+  const int cd = (d.f_dtype == LYCO_F32) ? LYCO_F32 : d.f_dtype;  // dtype the scale is computed in
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(idx / K);
+    const int k = static_cast<int>(idx % K);
+    const int ch = d.on_input ? (k / d.ia3_group) : n;
+    float s = rnd(ld_f(d.f0, d.f_dtype, ch) * d.m_post2, cd);
+    s = rnd(s + 1.f, cd);
+    const float w = cvt16(W[idx], d.w_dtype);
+    // product is formed in the promoted dtype (fp32 when the scale is fp32), then cast to W's dtype
+    Wout[idx] = to16(rnd(w * s, cd == LYCO_F32 ? LYCO_F32 : d.w_dtype), d.w_dtype);
+  }
+}
+
+// -------------------------------------------------------------- grad kernels --
+// Reduce this thread's G[4][8] patch against staged factors:
+//   ga[n, q] += sum_k G[n,k] * sb[q][k]     (gradient of the [N, r] factor)
+//   gb[q, k] += sum_n sa[n][q] * G[n,k]     (gradient of the [r, K'] factor)
+__device__ __forceinline__ void lr_grad_tile(const float (&G)[4][8], const float (*sa)[LR_RC],
+                                             const float (*sb)[LR_COLS], float* red /*[8][LR_COLS]*/,
+                                             int rc, int r0, int r, int N, int K, int n0, int k0,
+                                             float* ga, float* gb, float gb_scale) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int q = 0; q < rc; ++q) {
+    const float4 b0 = *reinterpret_cast<const float4*>(&sb[q][8 * lane]);
+    const float4 b1 = *reinterpret_cast<const float4*>(&sb[q][8 * lane + 4]);
+    float colsum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float s = G[i][0] * b0.x + G[i][1] * b0.y + G[i][2] * b0.z + G[i][3] * b0.w + G[i][4] * b1.x +
+                G[i][5] * b1.y + G[i][6] * b1.z + G[i][7] * b1.w;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const int n = n0 + 4 * warp + i;
+      if (lane == 0 && n < N) atomicAdd(&ga[static_cast<int64_t>(n) * r + r0 + q], s);
+      const float a = sa[4 * warp + i][q];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) colsum[j] = fmaf(a, G[i][j], colsum[j]);
+    }
+    // cross-warp reduction of the column sums through shared memory
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[warp * LR_COLS + 8 * lane + j] = colsum[j];
+    __syncthreads();
+    {
+      const int col = threadIdx.x;  // 256 threads <-> 256 columns
+      float s = 0.f;
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) s += red[w8 * LR_COLS + col];
+      if (k0 + col < K) atomicAdd(&gb[static_cast<int64_t>(r0 + q) * K + k0 + col], s * gb_scale);
+    }
+  }
+}
+
+template <bool LOHA>
+__global__ void __launch_bounds__(256) grad_lowrank_kernel(lyco_delta_desc_t d, const float* __restrict__ dW,
+                                                           float* g0, float* g1, float* g2, float* g3) {
+  __shared__ __align__(16) float sa[LR_ROWS][LR_RC];
+  __shared__ __align__(16) float sb[LR_RC][LR_COLS];
+  __shared__ __align__(16) float red[8 * LR_COLS];
+  const int N = d.out_dim, K = d.in_dim, r = d.rank;
+  const int k_tiles = (K + LR_COLS - 1) / LR_COLS;
+  const int n0 = (blockIdx.x / k_tiles) * LR_ROWS;
+  const int k0 = (blockIdx.x % k_tiles) * LR_COLS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int fround = d.pre_round ? d.pre_dtype : LYCO_F32;
+  const float gscale = d.m_pre * d.m_post1 * d.m_post2;
+
+  float G[4][8];
+  const int kc = k0 + 8 * lane;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int n = n0 + 4 * warp + i;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float g = 0.f;
+      if (n < N && kc + j < K) g = __ldg(&dW[static_cast<int64_t>(n) * K + kc + j]) * gscale;
+      G[i][j] = g;
+    }
+  }
+  if (!LOHA) {
+    for (int r0 = 0; r0 < r; r0 += LR_RC) {
+      const int rc = min(LR_RC, r - r0);
+      __syncthreads();
+      lr_stage_factors(d.f0, d.f1, d.f_dtype, N, K, r, n0, k0, r0, rc, sa, sb, fround, d.m_in);
+      __syncthreads();
+      lr_grad_tile(G, sa, sb, red, rc, r0, r, N, K, n0, k0, g0, g1, d.m_in);
+    }
+  } else {
+    // dP1 = G * P2, dP2 = G * P1   (functional/loha.py:18-30, recomputed instead of cached)
+    float P1[4][8], P2[4][8];
+    lr_product(P1, d.f0, d.f1, d.f_dtype, N, K, r, n0, k0, sa, sb, fround, 1.f);
+    lr_product(P2, d.f2, d.f3, d.f_dtype, N, K, r, n0, k0, sa, sb, fround, 1.f);
+    float G1[4][8], G2[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        G1[i][j] = G[i][j] * rnd(P2[i][j], fround);
+        G2[i][j] = G[i][j] * rnd(P1[i][j], fround);
+      }
+    for (int r0 = 0; r0 < r; r0 += LR_RC) {
+      const int rc = min(LR_RC, r - r0);
+      __syncthreads();
+      lr_stage_factors(d.f0, d.f1, d.f_dtype, N, K, r, n0, k0, r0, rc, sa, sb, fround, 1.f);
+      __syncthreads();
+      lr_grad_tile(G1, sa, sb, red, rc, r0, r, N, K, n0, k0, g0, g1, 1.f);
+      __syncthreads();
+      lr_stage_factors(d.f2, d.f3, d.f_dtype, N, K, r, n0, k0, r0, rc, sa, sb, fround, 1.f);
+      __syncthreads();
+      lr_grad_tile(G2, sa, sb, red, rc, r0, r, N, K, n0, k0, g2, g3, 1.f);
+    }
+  }
+}
+
+// LoKr: g_w1[pu,u] = sum_{pv,v} dW[pu*vp+pv, u*vq+v] * w2[pv,v]
+//       g_w2[pv,v] = sum_{pu,u} dW[...]              * w1[pu,u]
+// One CTA owns a strip of the (pv, v) plane and walks all (pu, u) blocks, so g_w2 needs no
+// atomics; g_w1 takes one atomic per warp per block.
+template <bool SMEM_W1>
+__global__ void __launch_bounds__(256) grad_lokr_kernel(lyco_delta_desc_t d, const float* __restrict__ dW,
+                                                        float* g_w1, float* g_w2) {
+  extern __shared__ float s_w1[];  // [up*uq] partial sums of g_w1 for this CTA (SMEM_W1 only)
+  const int K = d.in_dim;
+  const int n_w1 = d.up * d.uq;
+  if (SMEM_W1) {
+    for (int i = threadIdx.x; i < n_w1; i += blockDim.x) s_w1[i] = 0.f;
+    __syncthreads();
+  }
+  const int fround = d.pre_round ? d.pre_dtype : LYCO_F32;
+  const float gscale = d.m_pre * d.m_post1 * d.m_post2;
+  const int64_t plane = static_cast<int64_t>(d.vp) * d.vq;
+  const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool live = e < plane;
+  const int pv = live ? static_cast<int>(e / d.vq) : 0;
+  const int v = live ? static_cast<int>(e % d.vq) : 0;
+  const float b = live ? rnd(ld_f(d.f1, d.f_dtype, e), fround) : 0.f;
+  const int lane = threadIdx.x & 31;
+  float acc = 0.f;
+  for (int pu = 0; pu < d.up; ++pu) {
+    for (int u = 0; u < d.uq; ++u) {
+      float g = 0.f;
+      if (live)
+        g = __ldg(&dW[static_cast<int64_t>(pu * d.vp + pv) * K + static_cast<int64_t>(u) * d.vq + v]) * gscale;
+      const float a = rnd(ld_f(d.f0, d.f_dtype, pu * d.uq + u), fround);
+      acc = fmaf(a, g, acc);
+      float s = g * b;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) atomicAdd(SMEM_W1 ? &s_w1[pu * d.uq + u] : &g_w1[pu * d.uq + u], s);
+    }
+  }
+  if (live) g_w2[e] = acc;
+  if (SMEM_W1) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_w1; i += blockDim.x) atomicAdd(&g_w1[i], s_w1[i]);
+  }
+}
+
+// (IA)^3: g_w[c] = mult * sum dW[n,k] * W[n,k] over the row (or the input-channel columns)
+__global__ void __launch_bounds__(256) grad_ia3_kernel(lyco_delta_desc_t d, const float* __restrict__ dW,
+                                                       const uint16_t* __restrict__ W, float* g_w) {
+  const int K = d.in_dim, N = d.out_dim;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (!d.on_input) {
+    // one warp per output row
+    const int n = blockIdx.x * 8 + warp;
+    if (n >= N) return;
+    float s = 0.f;
+    for (int k = lane; k < K; k += 32)
+      s = fmaf(__ldg(&dW[static_cast<int64_t>(n) * K + k]), cvt16(W[static_cast<int64_t>(n) * K + k], d.w_dtype), s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) g_w[n] = s * d.m_post2;
+  } else {
+    // thread per column k, CTA covers a 64-row strip -> atomics across strips
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_begin = blockIdx.y * 64;
+    const int n_end = min(N, n_begin + 64);
+    if (k >= K) return;
+    float s = 0.f;
+    for (int n = n_begin; n < n_end; ++n)
+      s = fmaf(__ldg(&dW[static_cast<int64_t>(n) * K + k]), cvt16(W[static_cast<int64_t>(n) * K + k], d.w_dtype), s);
+    atomicAdd(&g_w[k / d.ia3_group], s * d.m_post2);
+  }
+}
+
+}  // namespace lyco

@@ -1,0 +1,138 @@
+"""Tensor-level wrappers over the C-ABI: device pointers, shapes and the current CUDA stream go in,
+nothing else.  PyTorch is used for memory and streams only; all arithmetic happens in the
+hand-written sm_100a kernels."""
+
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ALGO_DYLORA, ALGO_IA3, ALGO_LOCON, ALGO_LOHA, ALGO_LOKR, BF16, F16, F32, DeltaDesc
+
+_DT = {torch.bfloat16: BF16, torch.float16: F16, torch.float32: F32}
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    try:
+        return _DT[dt]
+    except KeyError:
+        raise TypeError(f"lycoris_b200: unsupported dtype {dt}") from None
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "lycoris_b200: the adapter hot path only exists as sm_100a CUDA kernels; "
+                f"got a {t.device.type} tensor (no CPU fallback)."
+            )
+
+
+def _stream() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def gemm_supported(*mats) -> bool:
+    """TMA needs 16-byte aligned bases and row pitches that are multiples of 8 elements."""
+    for t in mats:
+        if t.dim() != 2 or t.stride(1) != 1 or t.stride(0) % 8 or t.data_ptr() % 16:
+            return False
+        if t.dtype not in (torch.bfloat16, torch.float16):
+            return False
+    return True
+
+
+def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, out_dtype=None, split_k=0, out=None):
+    """``C[M,N] = A · Bᵀ (+ bias)``.
+
+    ``a`` is stored ``[M, K]`` (``a_mn=False``) or ``[K, M]`` (``a_mn=True``); likewise ``b`` with
+    ``N``.  Both must be row-contiguous 2-D tensors of the same 16-bit dtype.
+    """
+    _require_cuda(a, b, bias)
+    lib = _lib.load()
+    if a_mn:
+        K, M = a.shape
+    else:
+        M, K = a.shape
+    if b_mn:
+        Kb, N = b.shape
+    else:
+        N, Kb = b.shape
+    if K != Kb:
+        raise ValueError(f"lycoris_b200.gemm: reduction mismatch {K} vs {Kb}")
+    if a.dtype != b.dtype:
+        raise TypeError("lycoris_b200.gemm: operand dtypes differ")
+    out_dtype = out_dtype or a.dtype
+    if out is None:
+        out = torch.empty((M, N), device=a.device, dtype=out_dtype)
+    rc = lib.lyco_gemm(
+        _ptr(a), int(a_mn), a.stride(0),
+        _ptr(b), int(b_mn), b.stride(0),
+        _ptr(out), dtype_code(out.dtype), out.stride(0),
+        _ptr(bias), dtype_code(bias.dtype) if bias is not None else 0,
+        M, N, K, dtype_code(a.dtype), int(split_k), _stream(),
+    )
+    _lib.check(rc, "gemm")
+    return out
+
+
+def make_desc(algo, out_dim, in_dim, *, factors, w_dtype, rank=0, up=0, uq=0, vp=0, vq=0, on_input=0,
+              ia3_group=1, pre_round=0, pre_dtype=None, m_in=1.0, m_pre=1.0, m_post1=1.0, m_post2=1.0):
+    f = list(factors) + [None] * (4 - len(factors))
+    fd = None
+    for t in factors:
+        _require_cuda(t)
+        if not t.is_contiguous():
+            raise ValueError("lycoris_b200: factor tensors must be contiguous")
+        fd = fd or t.dtype
+        if t.dtype != fd:
+            raise TypeError("lycoris_b200: all factors of a layer must share a dtype")
+    d = DeltaDesc()
+    d.algo = algo
+    d.out_dim, d.in_dim, d.rank = int(out_dim), int(in_dim), int(rank)
+    d.up, d.uq, d.vp, d.vq = int(up), int(uq), int(vp), int(vq)
+    d.on_input, d.ia3_group = int(on_input), int(ia3_group)
+    d.f_dtype = dtype_code(fd)
+    d.w_dtype = dtype_code(w_dtype)
+    d.pre_round = int(pre_round)
+    d.pre_dtype = dtype_code(pre_dtype) if pre_dtype is not None else dtype_code(w_dtype)
+    d.m_in, d.m_pre, d.m_post1, d.m_post2 = float(m_in), float(m_pre), float(m_post1), float(m_post2)
+    d.f0, d.f1, d.f2, d.f3 = (None if t is None else t.data_ptr() for t in f)
+    d._keepalive = tuple(factors)  # keep the storages alive as long as the descriptor
+    return d
+
+
+def merge_weight(desc: DeltaDesc, W: torch.Tensor) -> torch.Tensor:
+    """``W' = W + ΔW`` with the reference's rounding points; one pass over ``W``."""
+    _require_cuda(W)
+    if not W.is_contiguous():
+        raise ValueError("lycoris_b200.merge_weight: W must be contiguous")
+    out = torch.empty_like(W)
+    rc = _lib.load().lyco_merge_weight(ctypes.byref(desc), _ptr(W), _ptr(out), _stream())
+    _lib.check(rc, "merge_weight")
+    return out
+
+
+def factor_grads(desc: DeltaDesc, dW: torch.Tensor, W, shapes):
+    """fp32 gradients of the factor arrays from fp32 ``dW' = dYᵀ·X``."""
+    _require_cuda(dW)
+    assert dW.dtype == torch.float32 and dW.is_contiguous()
+    gs = [torch.empty(s, device=dW.device, dtype=torch.float32) for s in shapes]
+    g = gs + [None] * (4 - len(gs))
+    rc = _lib.load().lyco_factor_grads(
+        ctypes.byref(desc), _ptr(dW), _ptr(W), _ptr(g[0]), _ptr(g[1]), _ptr(g[2]), _ptr(g[3]), _stream()
+    )
+    _lib.check(rc, "factor_grads")
+    return gs
+
+
+__all__ = [
+    "gemm", "gemm_supported", "make_desc", "merge_weight", "factor_grads", "dtype_code",
+    "ALGO_LOCON", "ALGO_LOHA", "ALGO_LOKR", "ALGO_IA3", "ALGO_DYLORA", "BF16", "F16", "F32",
+]

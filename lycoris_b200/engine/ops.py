@@ -1,0 +1,300 @@
+"""The fused adapter layer: autograd functions that replace the reference's rebuild-mode forward
+(lycoris/modules/locon.py:317-332 and its siblings) with
+
+    forward   W' = merge(W, factors)                 one HBM pass      (lyco_merge_weight)
+              Y  = X · W'ᵀ + b                        one contraction   (lyco_gemm, tcgen05)
+    backward  dX  = dY · W'                           one contraction
+              dW' = dYᵀ · X   (fp32, split over M)    one contraction
+              d(factors) from dW'                     one HBM pass      (lyco_factor_grads)
+
+i.e. 1 + 2 dense contractions where the reference runs 2 + 3, no N×K temporaries besides W'
+itself, and ~6 launches per layer-step instead of 35–60 ATen ops.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import torch
+import torch.nn.functional as F
+
+from ..logging import warning_once
+from . import kernels as K
+from ._lib import EngineUnavailable
+
+_HALF = (torch.bfloat16, torch.float16)
+
+
+@dataclass
+class NativeSpec:
+    """What the merge / gradient kernels need to know about one adapter (see lyco_delta_desc_t)."""
+
+    algo: int
+    factors: tuple
+    rank: int = 0
+    up: int = 0
+    uq: int = 0
+    vp: int = 0
+    vq: int = 0
+    on_input: int = 0
+    ia3_group: int = 1
+    matmul_product: bool = True  # factor product is an autocast-eligible matmul (locon/loha/dylora)
+    m_in: float = 1.0
+    m_pre: float = 1.0
+    m_post1: float = 1.0
+    m_post2: float = 1.0
+    grad_mask: tuple = field(default_factory=tuple)  # optional per-factor "needs grad" override
+
+
+def _autocast_dtype():
+    if torch.is_autocast_enabled("cuda"):
+        return torch.get_autocast_dtype("cuda")
+    return None
+
+
+def _build_desc(spec: NativeSpec, factors, w_dtype, ac_dtype, out_dim, in_dim):
+    fdt = factors[0].dtype
+    prod_dtype = ac_dtype if (ac_dtype is not None and spec.matmul_product) else fdt
+    pre_round = prod_dtype in _HALF
+    return K.make_desc(
+        spec.algo, out_dim, in_dim, factors=factors, w_dtype=w_dtype, rank=spec.rank,
+        up=spec.up, uq=spec.uq, vp=spec.vp, vq=spec.vq, on_input=spec.on_input, ia3_group=spec.ia3_group,
+        pre_round=int(pre_round), pre_dtype=prod_dtype if pre_round else w_dtype,
+        m_in=spec.m_in, m_pre=spec.m_pre, m_post1=spec.m_post1, m_post2=spec.m_post2,
+    )
+
+
+def _uniform_factors(factors):
+    """The kernels take one factor dtype per layer; mixed dtypes promote to fp32 (exact)."""
+    dts = {f.dtype for f in factors}
+    if len(dts) == 1:
+        return tuple(f.contiguous() for f in factors)
+    return tuple(f.float().contiguous() for f in factors)
+
+
+# --------------------------------------------------------------------------- dense
+def _dense_nt(a, b, bias=None):
+    """a[M,K] · b[N,K]ᵀ (+ bias) — forward contraction."""
+    if K.gemm_supported(a, b):
+        return K.gemm(a, b, bias=bias)
+    warning_once("lycoris_b200: a layer shape is not TMA-addressable (needs multiples of 8); "
+                 "that layer's contraction uses the library GEMM")
+    return F.linear(a, b, bias)
+
+
+def _dense_nn(a, b):
+    """a[M,N] · b[N,K] — dgrad contraction (b consumed MN-major, no transpose copy)."""
+    if K.gemm_supported(a, b):
+        return K.gemm(a, b, b_mn=True)
+    return a @ b
+
+
+def _dense_tn_f32(a, b):
+    """a[M,N]ᵀ · b[M,K] -> fp32 [N,K] — wgrad contraction, reduction split across CTAs."""
+    if K.gemm_supported(a, b):
+        return K.gemm(a, b, a_mn=True, b_mn=True, out_dtype=torch.float32)
+    return (a.t() @ b).float()
+
+
+def _conv_forward(x, w, bias, cp):
+    return torch.ops.aten.convolution(x, w, bias, cp["stride"], cp["padding"], cp["dilation"], False,
+                                      [0] * len(cp["stride"]), cp["groups"])
+
+
+def _conv_backward(dy, x, w, cp, need_x, need_w):
+    dx, dw, _ = torch.ops.aten.convolution_backward(
+        dy, x, w, None, cp["stride"], cp["padding"], cp["dilation"], False, [0] * len(cp["stride"]),
+        cp["groups"], [need_x, need_w, False])
+    return dx, dw
+
+
+def _is_pointwise(cp, w):
+    """1x1 / stride 1 / no padding convolution == linear over channels."""
+    return (w.dim() == 4 and w.shape[2] == 1 and w.shape[3] == 1 and tuple(cp["stride"]) == (1, 1)
+            and tuple(cp["padding"]) == (0, 0) and cp["groups"] == 1)
+
+
+# ------------------------------------------------------------------ autograd nodes
+class _AdapterContraction(torch.autograd.Function):
+    """y = op(x, merge(W, factors), bias) with everything on the sm_100a kernels."""
+
+    @staticmethod
+    def forward(ctx, x, W, bias, spec, conv, delta_only, ac_dtype, *factors):
+        factors_u = _uniform_factors(factors)
+        out_dim = W.shape[0]
+        in_dim = W.numel() // out_dim
+        desc = _build_desc(spec, factors_u, W.dtype, ac_dtype, out_dim, in_dim)
+        Wm = K.merge_weight(desc, W)
+        if delta_only:
+            Wm = Wm - W  # exact on W's grid: this is the reference's `new_weight - base_weight`
+        if conv is None:
+            x2 = x.reshape(-1, x.shape[-1])
+            if not x2.is_contiguous():
+                x2 = x2.contiguous()
+            y = _dense_nt(x2, Wm, bias).view(*x.shape[:-1], out_dim)
+        else:
+            y = _conv_forward(x, Wm, bias, conv)
+        ctx.save_for_backward(x, W, Wm, *factors)
+        ctx.spec, ctx.conv, ctx.ac_dtype = spec, conv, ac_dtype
+        ctx.dims = (out_dim, in_dim)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W, Wm, *factors = ctx.saved_tensors
+        spec, conv = ctx.spec, ctx.conv
+        out_dim, in_dim = ctx.dims
+        need_x = ctx.needs_input_grad[0]
+        need_f = any(ctx.needs_input_grad[7:])
+        dx = None
+        dWm = None
+        if conv is None:
+            dy2 = dy.reshape(-1, out_dim)
+            if not dy2.is_contiguous():
+                dy2 = dy2.contiguous()
+            if need_x:
+                dx = _dense_nn(dy2, Wm).view(x.shape)
+            if need_f:
+                x2 = x.reshape(-1, x.shape[-1])
+                if not x2.is_contiguous():
+                    x2 = x2.contiguous()
+                dWm = _dense_tn_f32(dy2, x2)
+        else:
+            dyc = dy.contiguous()
+            dx, dw = _conv_backward(dyc, x, Wm, conv, need_x, need_f)
+            if need_f:
+                dWm = dw.reshape(out_dim, in_dim).float()
+        grads = [None] * len(factors)
+        if need_f:
+            factors_u = _uniform_factors(factors)
+            desc = _build_desc(spec, factors_u, W.dtype, ctx.ac_dtype, out_dim, in_dim)
+            gs = K.factor_grads(desc, dWm.contiguous(), W, [f.shape for f in factors_u])
+            for i, (g, f) in enumerate(zip(gs, factors)):
+                if ctx.needs_input_grad[7 + i]:
+                    grads[i] = g.to(f.dtype) if g.dtype != f.dtype else g
+        return (dx, None, None, None, None, None, None, *grads)
+
+
+class _MergedContraction(torch.autograd.Function):
+    """y = op(x, Wm, bias) where Wm was assembled by PyTorch ops (DoRA / Tucker / scalar / dropout
+    variants): only the three dense contractions run in the engine; dWm goes back to autograd."""
+
+    @staticmethod
+    def forward(ctx, x, Wm, bias, conv):
+        if conv is None:
+            x2 = x.reshape(-1, x.shape[-1])
+            if not x2.is_contiguous():
+                x2 = x2.contiguous()
+            y = _dense_nt(x2, Wm.contiguous(), bias).view(*x.shape[:-1], Wm.shape[0])
+        else:
+            y = _conv_forward(x, Wm, bias, conv)
+        ctx.save_for_backward(x, Wm)
+        ctx.conv = conv
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, Wm = ctx.saved_tensors
+        conv = ctx.conv
+        need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        dx = dw = None
+        if conv is None:
+            dy2 = dy.reshape(-1, Wm.shape[0])
+            if not dy2.is_contiguous():
+                dy2 = dy2.contiguous()
+            if need_x:
+                dx = _dense_nn(dy2, Wm.contiguous()).view(x.shape)
+            if need_w:
+                x2 = x.reshape(-1, x.shape[-1])
+                if not x2.is_contiguous():
+                    x2 = x2.contiguous()
+                dw = _dense_tn_f32(dy2, x2).to(Wm.dtype)
+        else:
+            dx, dw = _conv_backward(dy.contiguous(), x, Wm, conv, need_x, need_w)
+        return dx, dw, None, None
+
+
+# --------------------------------------------------------------------- dispatcher
+def _conv_params(module):
+    kw = module.kw_dict
+    return {
+        "stride": list(kw["stride"]),
+        "padding": list(kw["padding"]) if not isinstance(kw["padding"], str) else kw["padding"],
+        "dilation": list(kw["dilation"]),
+        "groups": kw["groups"],
+    }
+
+
+def adapter_forward(module, x, args, kwargs, native_spec, assemble_fallback):
+    """Rebuild-mode forward of one adapter on the engine (called from ``Module.forward``)."""
+    if not x.is_cuda:
+        raise EngineUnavailable(
+            "lycoris_b200: the adapter forward/backward hot path exists only as sm_100a CUDA kernels; "
+            f"got a {x.device.type} input for {module.lora_name!r}. There is no CPU fallback — "
+            "use the reference implementation for CPU runs."
+        )
+    org = module.org_module[0]
+    W = org.weight.detach()
+    bias = None if org.bias is None else org.bias.detach()
+    ac = _autocast_dtype()
+    cdt = ac if ac is not None else W.dtype
+    if cdt not in _HALF:
+        raise NotImplementedError(
+            f"lycoris_b200: compute dtype {cdt} — the engine contracts bf16/fp16 operands "
+            "(fp32 accumulation); cast the base model to bf16/fp16 or run under torch.autocast"
+        )
+    if W.dtype != cdt:
+        W = W.to(cdt)
+    if bias is not None and bias.dtype != cdt:
+        bias = bias.to(cdt)
+    if x.dtype != cdt:
+        if ac is None:
+            raise RuntimeError(f"lycoris_b200: input dtype {x.dtype} != weight dtype {cdt} (no autocast active)")
+        x = x.to(cdt)
+    if not W.is_contiguous():
+        W = W.contiguous()
+
+    is_conv = module.module_type.startswith("conv")
+    conv = _conv_params(module) if is_conv else None
+    if is_conv and isinstance(conv["padding"], str):
+        raise NotImplementedError("lycoris_b200: string padding modes are not supported")
+    if is_conv and _is_pointwise(conv, W) and x.is_contiguous(memory_format=torch.channels_last) and x.dim() == 4:
+        # NHWC 1x1 convolution is a plain linear over channels: run it on the tcgen05 GEMM
+        y = adapter_forward_pointwise(module, x, W, bias, ac, native_spec, assemble_fallback, args, kwargs)
+        return y
+
+    plain = module._is_outermost_on_plain_forward() and not args and not kwargs
+    base = None
+    if not plain:
+        # another wrapper sits below us (stacking) or the base forward takes extra arguments:
+        # keep its output and add only our delta contraction, like the reference does.
+        base = module.org_forward(x, *args, **kwargs)
+
+    spec = native_spec()
+    if spec is not None:
+        y = _AdapterContraction.apply(x, W, None if not plain else bias, spec, conv, not plain, ac, *spec.factors)
+    else:
+        Wm = assemble_fallback(W)
+        if not plain:
+            Wm = Wm - W
+        y = _MergedContraction.apply(x, Wm, None if not plain else bias, conv)
+    return y if plain else base + y
+
+
+def adapter_forward_pointwise(module, x, W, bias, ac, native_spec, assemble_fallback, args, kwargs):
+    """channels_last 1x1 conv: [B,C,H,W] (NHWC storage) -> [B*H*W, C] linear -> NHWC output."""
+    B, C, H, Wd = x.shape
+    plain = module._is_outermost_on_plain_forward() and not args and not kwargs
+    base = None if plain else module.org_forward(x, *args, **kwargs)
+    x2 = x.permute(0, 2, 3, 1).reshape(B * H * Wd, C)
+    W2 = W.reshape(W.shape[0], C)
+    spec = native_spec()
+    if spec is not None:
+        y2 = _AdapterContraction.apply(x2, W2, bias if plain else None, spec, None, not plain, ac, *spec.factors)
+    else:
+        Wm = assemble_fallback(W).reshape(W.shape[0], C)
+        if not plain:
+            Wm = Wm - W2
+        y2 = _MergedContraction.apply(x2, Wm, bias if plain else None, None)
+    y = y2.view(B, H, Wd, W.shape[0]).permute(0, 3, 1, 2)
+    return y if plain else base + y
