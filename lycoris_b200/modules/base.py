@@ -379,6 +379,7 @@ class LycorisBaseModule(ModuleCustomSD):
     def _reset_scalar_after_load(self, incompatible_keys):
         """Checkpoints carry the scalar folded into the first factor: drop the missing-key report
         and reset the live scalar to 1 (locon.py:184-196)."""
+        self._scalar_cache = None
         missing = incompatible_keys.missing_keys
         for key in [k for k in missing if "scalar" in k]:
             missing.remove(key)
@@ -388,6 +389,15 @@ class LycorisBaseModule(ModuleCustomSD):
             self.scalar.copy_(torch.ones_like(self.scalar))
         else:
             self.register_buffer("scalar", torch.ones_like(self.scalar), persistent=False)
+
+    def _scalar_host(self):
+        """Host copy of the (non-trainable) scalar buffer; cached so the hot path never syncs.
+        ``apply_max_norm`` and checkpoint loads invalidate it."""
+        v = getattr(self, "_scalar_cache", None)
+        if v is None:
+            v = float(self.scalar)
+            self._scalar_cache = v
+        return v
 
     def _module_dropped(self):
         return bool(self.module_dropout and self.training and torch.rand(1) < self.module_dropout)

@@ -1,0 +1,92 @@
+"""Shared helpers for the parity tests: build product modules from golden cases, run the oracle."""
+import os
+import random
+
+import torch
+import torch.nn as nn
+
+from conftest import GOLDEN
+
+_CACHE = {}
+
+
+def load_cases(regime):
+    if regime not in _CACHE:
+        _CACHE[regime] = torch.load(os.path.join(GOLDEN, f"layers_{regime}.pt"), weights_only=False)
+    return _CACHE[regime]
+
+
+def case_ids(regime):
+    return sorted(load_cases(regime).keys())
+
+
+def build_base(case, device="cpu"):
+    spec = case["meta"]["layer_spec"]
+    if spec["kind"] == "linear":
+        base = nn.Linear(spec["in_dim"], spec["out_dim"])
+    else:
+        base = nn.Conv2d(spec["in_dim"], spec["out_dim"], spec["k"], spec["stride"], spec["pad"])
+    base.weight.data = case["weight"].clone()
+    base.bias.data = case["bias"].clone()
+    for p in base.parameters():
+        p.requires_grad_(False)
+    return base.to(device)
+
+
+def build_product_module(case, base):
+    """lycoris_b200 module with the golden case's parameters (same constructor call as the reference)."""
+    import lycoris_b200.modules as M
+    from lycoris_b200.modules import dylora, ia3  # noqa: F401
+
+    meta = case["meta"]
+    cls = {"LoConModule": M.LoConModule, "LohaModule": M.LohaModule, "LokrModule": M.LokrModule,
+           "IA3Module": M.IA3Module, "DyLoraModule": M.DyLoraModule}[meta["cls"]]
+    mod = cls("case", base, 1.0, meta["dim"], meta["alpha"], 0.0, 0.0, 0.0, False, **meta["kw"])
+    own = dict(mod.named_parameters())
+    assert set(own) == set(case["params"]), (sorted(own), sorted(case["params"]))
+    with torch.no_grad():
+        for k, v in case["params"].items():
+            assert own[k].shape == v.shape, (k, own[k].shape, v.shape)
+            own[k].data = v.clone().to(own[k].device)
+    return mod
+
+
+def oracle_args(case, device="cpu"):
+    """(algo, params, cfg, conv) for oracle.lyco_oracle.layer_forward_backward."""
+    meta = case["meta"]
+    key = meta["algo_key"]
+    p = {k: v.to(device) for k, v in case["params"].items()}
+    cfg = {"multiplier": 1.0, "scale": meta["scale"]}
+    if key == "locon":
+        algo = "locon"
+    elif key == "loha":
+        algo = "loha"
+    elif key.startswith("lokr"):
+        algo = "lokr"
+    elif key.startswith("ia3"):
+        algo = "ia3"
+        cfg["train_on_input"] = meta["kw"]["train_on_input"]
+    else:
+        algo = "dylora"
+        nb = meta["dim"] // meta["kw"]["block_size"]
+        p = {"up_list": [p[f"up_list.{i}"] for i in range(nb)], "down_list": [p[f"down_list.{i}"] for i in range(nb)]}
+        cfg["alpha"] = torch.tensor(meta["alpha"], device=device)
+        cfg["b"] = meta["dylora_b"]
+    spec = meta["layer_spec"]
+    conv = None
+    if spec["kind"] == "conv":
+        conv = dict(stride=(spec["stride"],) * 2, padding=(spec["pad"],) * 2, dilation=(1, 1), groups=1)
+    return algo, p, cfg, conv
+
+
+def flat_grads(case_grads):
+    return {k: v for k, v in case_grads.items()}
+
+
+def rel_err(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).norm() / (b.norm() + 1e-12))
+
+
+def seed_dylora(case):
+    random.seed(case["meta"]["dylora_seed"])
