@@ -48,6 +48,15 @@ def gemm_supported(*mats) -> bool:
     return True
 
 
+_gemm_profile = None  # bench.py: list collecting (start_event, end_event, flops, M, N, K) per launch
+
+
+def set_gemm_profiler(sink):
+    """Record a CUDA-event pair around every GEMM launch into ``sink`` (None disables)."""
+    global _gemm_profile
+    _gemm_profile = sink
+
+
 def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, out_dtype=None, split_k=0, out=None):
     """``C[M,N] = A · Bᵀ (+ bias)``.
 
@@ -71,6 +80,11 @@ def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, out_dtype=None, split_k=0, 
     out_dtype = out_dtype or a.dtype
     if out is None:
         out = torch.empty((M, N), device=a.device, dtype=out_dtype)
+    prof = _gemm_profile
+    if prof is not None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = lib.lyco_gemm(
         _ptr(a), int(a_mn), a.stride(0),
         _ptr(b), int(b_mn), b.stride(0),
@@ -79,6 +93,9 @@ def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, out_dtype=None, split_k=0, 
         M, N, K, dtype_code(a.dtype), int(split_k), _stream(),
     )
     _lib.check(rc, "gemm")
+    if prof is not None:
+        e1.record()
+        prof.append((e0, e1, 2.0 * M * N * K, M, N, K))
     return out
 
 

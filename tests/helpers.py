@@ -90,3 +90,49 @@ def rel_err(a, b):
 
 def seed_dylora(case):
     random.seed(case["meta"]["dylora_seed"])
+
+
+def oracle_patch_network(net):
+    """Route every wrapped layer of a (not applied) lycoris_b200 network through the ORACLE's
+    per-layer forward using the network's own parameter tensors — a reference-equivalent eager
+    network on whatever device the model lives on.  Returns an undo callable."""
+    import random as _random
+
+    from oracle import lyco_oracle as O
+
+    undo = []
+    for lora in net.loras:
+        org = lora.org_module[0]
+        conv = None
+        if lora.module_type.startswith("conv"):
+            conv = dict(stride=org.stride, padding=org.padding, dilation=org.dilation, groups=org.groups)
+        cls = type(lora).__name__
+
+        def fwd(x, _l=lora, _o=org, _c=conv, _cls=cls):
+            p = dict(_l.named_parameters())
+            cfg = {"multiplier": _l.multiplier, "scale": getattr(_l, "scale", 1.0)}
+            if _cls == "LoConModule":
+                algo = "locon"
+            elif _cls == "LohaModule":
+                algo = "loha"
+            elif _cls == "LokrModule":
+                algo = "lokr"
+            elif _cls == "IA3Module":
+                algo = "ia3"
+                cfg["train_on_input"] = _l.train_input
+            else:
+                algo = "dylora"
+                p = {"up_list": list(_l.up_list), "down_list": list(_l.down_list)}
+                cfg["alpha"] = _l.alpha
+                cfg["b"] = _random.randint(0, _l.block_count - 1)
+            return O.layer_forward(algo, x, _o.weight, _o.bias, p, cfg, _c)
+
+        saved = org.forward
+        org.forward = fwd
+        undo.append((org, saved))
+
+    def restore():
+        for org, saved in undo:
+            org.forward = saved
+
+    return restore

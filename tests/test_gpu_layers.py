@@ -1,0 +1,182 @@
+"""GPU parity, per wrapped layer: the CUDA engine (through the public module API -> C-ABI) against
+(a) the committed reference outputs in tests/golden and (b) the oracle run on the same device.
+
+Tolerances (stated against the REFERENCE, whose own bf16 path rounds the base and delta
+contractions separately and snaps dW onto W's bf16 grid):
+  y, dx      : |err| <= 2^-6 * max|ref|   (two bf16 ulps at the tensor's scale) and mse < 5e-4,
+               the bound the reference's own test/functional.py:12-16 uses for bf16;
+  param grads: relative Frobenius error <= 3e-2 (sums of ~1e3 bf16-rounded products).
+"""
+import random
+
+import pytest
+import torch
+
+from helpers import build_base, build_product_module, case_ids, load_cases, oracle_args, rel_err, seed_dylora
+
+pytestmark = pytest.mark.gpu
+
+Y_REL = 2.0 ** -6
+G_REL = 3e-2
+
+
+def _run_engine(case, regime):
+    dev = "cuda"
+    base = build_base(case, dev)
+    mod = build_product_module(case, base).to(dev)
+    if regime == "bf16":
+        base.to(torch.bfloat16)
+        mod.to(torch.bfloat16)
+    elif regime == "autocast_bf16":
+        base.to(torch.bfloat16)
+    mod.apply_to()
+    mod.train()
+    x = case["x"].to(dev).clone().requires_grad_(True)
+    seed_dylora(case)
+    if regime == "autocast_bf16":
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = base(x)
+    else:
+        y = base(x)
+    y.backward(case["dy"].to(dev).to(y.dtype))
+    grads = {k: v.grad for k, v in mod.named_parameters() if v.grad is not None}
+    mod.restore()
+    return y.detach(), x.grad, grads
+
+
+def _check(name, y, dx, grads, ref_y, ref_dx, ref_grads):
+    for tag, a, b in (("y", y, ref_y), ("dx", dx, ref_dx)):
+        a, b = a.float().cpu(), b.float().cpu()
+        bound = Y_REL * float(b.abs().max())
+        err = float((a - b).abs().max())
+        assert err <= bound, (name, tag, err, bound)
+        assert float(((a - b) ** 2).mean()) < 5e-4, (name, tag)
+    assert set(grads) == set(ref_grads), (name, sorted(grads), sorted(ref_grads))
+    for k, g in ref_grads.items():
+        e = rel_err(grads[k].cpu(), g.cpu())
+        assert e <= G_REL, (name, k, e)
+
+
+@pytest.mark.parametrize("regime", ["bf16", "autocast_bf16"])
+def test_engine_matches_reference_fixtures(regime):
+    cases = load_cases(regime)
+    worst = 0.0
+    for name in case_ids(regime):
+        case = cases[name]
+        y, dx, grads = _run_engine(case, regime)
+        assert y.dtype == case["y"].dtype
+        _check(name, y, dx, grads, case["y"], case["dx"], case["grads"])
+        worst = max(worst, float((y.float().cpu() - case["y"].float()).abs().max()))
+    print(f"[{regime}] 32 cases, worst |y - y_ref| = {worst:.4g}")
+
+
+@pytest.mark.parametrize("regime", ["bf16", "autocast_bf16"])
+def test_engine_matches_oracle_on_device(regime):
+    """Same comparison with the oracle evaluated on the GPU (cuBLAS/cuDNN eager, like the reference
+    would run there) — isolates device-kernel differences from CPU-vs-GPU library differences."""
+    from oracle import lyco_oracle as O
+
+    cases = load_cases(regime)
+    ac = torch.bfloat16 if regime == "autocast_bf16" else None
+    for name in case_ids(regime):
+        case = cases[name]
+        algo, p, cfg, conv = oracle_args(case, "cuda")
+        oy, odx, og = O.layer_forward_backward(algo, case["x"].cuda(), case["weight"].cuda(), case["bias"].cuda(),
+                                               p, cfg, case["dy"].cuda(), conv, ac)
+        ref_grads = {}
+        for k, g in og.items():
+            if isinstance(g, list):
+                for i, t in enumerate(g):
+                    if t is not None:
+                        ref_grads[f"{k}.{i}"] = t
+            elif g is not None:
+                ref_grads[k] = g
+        y, dx, grads = _run_engine(case, regime)
+        _check(name, y, dx, grads, oy, odx, ref_grads)
+
+
+def test_fp32_base_is_refused_loudly():
+    """cfg #1 regime (fp32 everywhere, no autocast) is the reference's CPU case; the engine
+    contracts 16-bit operands only and says so instead of silently down-casting."""
+    case = load_cases("fp32")["locon/linear"]
+    base = build_base(case, "cuda")
+    mod = build_product_module(case, base).cuda()
+    mod.apply_to()
+    with pytest.raises(NotImplementedError):
+        base(case["x"].cuda())
+    mod.restore()
+
+
+def test_fp32_base_under_autocast_runs():
+    """fp32 base weights + fp32 adapter under torch.autocast(bf16): operands are cast to bf16 like
+    autocast would do for F.linear; compared with the oracle under the same autocast."""
+    from oracle import lyco_oracle as O
+
+    cases = load_cases("fp32")
+    for name in ("locon/linear", "lokr_full/linear", "loha/conv3", "ia3_out/linear"):
+        case = cases[name]
+        algo, p, cfg, conv = oracle_args(case, "cuda")
+        oy, odx, og = O.layer_forward_backward(algo, case["x"].cuda(), case["weight"].cuda(), case["bias"].cuda(),
+                                               p, cfg, case["dy"].cuda(), conv, torch.bfloat16)
+        base = build_base(case, "cuda")
+        mod = build_product_module(case, base).cuda()
+        mod.apply_to()
+        x = case["x"].cuda().requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = base(x)
+        y.backward(case["dy"].cuda().to(y.dtype))
+        mod.restore()
+        assert float((y.float() - oy.float()).abs().max()) <= Y_REL * float(oy.float().abs().max()), name
+        assert float((x.grad.float() - odx.float()).abs().max()) <= Y_REL * float(odx.float().abs().max()) + 1e-6, name
+
+
+def test_stacked_wrappers_are_additive():
+    """test/wrapper.py:233-287 of the reference: stacked == base + delta1 + delta2."""
+    import torch.nn as nn
+
+    import lycoris_b200 as L
+
+    torch.manual_seed(0)
+    base = nn.Linear(64, 96).cuda().to(torch.bfloat16)
+    for p in base.parameters():
+        p.requires_grad_(False)
+    x = torch.randn(4, 7, 64, device="cuda", dtype=torch.bfloat16)
+    y0 = base(x)
+    a = L.LoConModule("a", base, 1.0, 4, 2).cuda().to(torch.bfloat16)
+    b = L.LokrModule("b", base, 1.0, 100000, 1, factor=4).cuda().to(torch.bfloat16)
+    with torch.no_grad():
+        a.lora_up.weight.normal_(0, 0.05)
+        b.lokr_w2.normal_(0, 0.05)
+    a.apply_to()
+    ya = base(x)
+    a.restore()
+    b.apply_to()
+    yb = base(x)
+    b.restore()
+    a.apply_to()
+    b.apply_to()
+    yab = base(x)
+    b.restore()
+    a.restore()
+    expect = y0.float() + (ya.float() - y0.float()) + (yb.float() - y0.float())
+    assert float((yab.float() - expect).abs().max()) <= 2 * Y_REL * float(expect.abs().max())
+    assert torch.equal(base(x), y0)
+
+
+def test_zero_init_adapter_is_identity_and_engine_was_used():
+    import torch.nn as nn
+
+    import lycoris_b200 as L
+    from lycoris_b200.engine import _lib
+
+    base = nn.Linear(128, 128).cuda().to(torch.bfloat16)
+    x = torch.randn(32, 128, device="cuda", dtype=torch.bfloat16)
+    y0 = base(x)
+    before = _lib.launch_count()
+    m = L.LoConModule("a", base, 1.0, 8, 4).cuda().to(torch.bfloat16)
+    m.apply_to()
+    y1 = base(x)
+    m.restore()
+    assert _lib.launch_count() >= before + 2, "the CUDA extension did not run"
+    # dW == 0 -> W' == W exactly; single fp32-accumulated contraction vs cuBLAS: <= 1 bf16 ulp apart
+    assert float((y1.float() - y0.float()).abs().max()) <= 2.0 ** -7 * float(y0.float().abs().max())
