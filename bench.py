@@ -175,6 +175,10 @@ def run_engine(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     assert _lib.load().lyco_device_check(local_rank) == 0, _lib.last_error()
+    # Everything runs on one non-default stream: autograd binds each parameter's AccumulateGrad node to
+    # the stream of its first use, and a node bound to the legacy default stream cannot be captured.
+    main_stream = torch.cuda.Stream(device=device)
+    torch.cuda.set_stream(main_stream)
 
     unet, net, f1, n_layers = build_engine_workload(args, device)
     n_params = sum(p.numel() for p in net.parameters())
@@ -205,12 +209,6 @@ def run_engine(args):
     static_loss = None
     if not args.no_graph:
         try:
-            s = torch.cuda.Stream()
-            s.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(s):
-                step()
-            torch.cuda.current_stream().wait_stream(s)
-            torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 static_loss = step()
@@ -247,7 +245,7 @@ def run_engine(args):
             if e2e:
                 for k, v in host.items():
                     static[k].copy_(v, non_blocking=True)
-                last = float(one_step())  # device -> host read of the step's result
+                last = float(one_step().detach())  # device -> host read of the step's result
             else:
                 last = one_step()
         e1.record()

@@ -68,6 +68,90 @@ __device__ __forceinline__ uint32_t pack16(float a, float b, int fmt) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// Epilogue for one 32-column chunk of one accumulator row held in registers (fp32 bit patterns).
+template <int EPI>
+__device__ __forceinline__ void store_chunk(const uint32_t (&r)[32], int row, int col0, const GemmParams& p) {
+  if (row >= p.M || col0 >= p.N) return;
+  const bool full = (col0 + 32 <= p.N);
+  if (EPI == EPI_STORE16) {
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    if (p.bias != nullptr) {
+      if (full && p.bias_dtype != 2 && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {
+        // 32 x 16-bit bias values = four 16-byte loads (every lane reads the same addresses: L1 broadcast)
+        const uint4* bp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.bias) + col0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint4 bv = __ldg(bp + q);
+          const uint32_t w[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            float lo, hi;
+            if (p.bias_dtype == 0) {
+              lo = __uint_as_float(w[t] << 16);
+              hi = __uint_as_float(w[t] & 0xFFFF0000u);
+            } else {
+              const __half2 h = *reinterpret_cast<const __half2*>(&w[t]);
+              lo = __low2float(h);
+              hi = __high2float(h);
+            }
+            v[8 * q + 2 * t] += lo;
+            v[8 * q + 2 * t + 1] += hi;
+          }
+        }
+      } else if (full) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += load_scalar(p.bias, p.bias_dtype, col0 + j);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < p.N) v[j] += load_scalar(p.bias, p.bias_dtype, col0 + j);
+      }
+    }
+    uint16_t* crow = reinterpret_cast<uint16_t*>(p.C) + static_cast<int64_t>(row) * p.ldc + col0;
+    if (full) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 o;
+        o.x = pack16(v[8 * q + 0], v[8 * q + 1], p.fmt);
+        o.y = pack16(v[8 * q + 2], v[8 * q + 3], p.fmt);
+        o.z = pack16(v[8 * q + 4], v[8 * q + 5], p.fmt);
+        o.w = pack16(v[8 * q + 6], v[8 * q + 7], p.fmt);
+        reinterpret_cast<uint4*>(crow)[q] = o;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < p.N) crow[j] = static_cast<uint16_t>(pack16(v[j], 0.f, p.fmt) & 0xFFFF);
+    }
+  } else {
+    float* crow = reinterpret_cast<float*>(p.C) + static_cast<int64_t>(row) * p.ldc + col0;
+    if (full) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (EPI == EPI_STORE_F32) {
+          reinterpret_cast<float4*>(crow)[q] =
+              make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                          __uint_as_float(r[4 * q + 3]));
+        } else {
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow + 4 * q),
+                       "f"(__uint_as_float(r[4 * q])), "f"(__uint_as_float(r[4 * q + 1])),
+                       "f"(__uint_as_float(r[4 * q + 2])), "f"(__uint_as_float(r[4 * q + 3]))
+                       : "memory");
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < p.N) {
+          if (EPI == EPI_STORE_F32) crow[j] = __uint_as_float(r[j]);
+          else atomicAdd(crow + j, __uint_as_float(r[j]));
+        }
+    }
+  }
+}
+
 template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
@@ -206,64 +290,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
         }
-        const int col0 = n_idx * BLOCK_N + c * 32;
-        if (row >= p.M || col0 >= p.N) continue;
-        const bool full = (col0 + 32 <= p.N);
-        if (EPI == EPI_STORE16) {
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (p.bias != nullptr) {
-            if (full) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] += load_scalar(p.bias, p.bias_dtype, col0 + j);
-            } else {
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) v[j] += load_scalar(p.bias, p.bias_dtype, col0 + j);
-            }
-          }
-          uint16_t* crow = reinterpret_cast<uint16_t*>(p.C) + static_cast<int64_t>(row) * p.ldc + col0;
-          if (full) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 o;
-              o.x = pack16(v[8 * q + 0], v[8 * q + 1], p.fmt);
-              o.y = pack16(v[8 * q + 2], v[8 * q + 3], p.fmt);
-              o.z = pack16(v[8 * q + 4], v[8 * q + 5], p.fmt);
-              o.w = pack16(v[8 * q + 6], v[8 * q + 7], p.fmt);
-              reinterpret_cast<uint4*>(crow)[q] = o;
-            }
-          } else {
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) {
-                const uint32_t pk = pack16(v[j], 0.f, p.fmt);
-                crow[j] = static_cast<uint16_t>(pk & 0xFFFF);
-              }
-          }
-        } else {
-          float* crow = reinterpret_cast<float*>(p.C) + static_cast<int64_t>(row) * p.ldc + col0;
-          if (full) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              if (EPI == EPI_STORE_F32) {
-                float4 o = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
-                                       __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
-                reinterpret_cast<float4*>(crow)[q] = o;
-              } else {
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow + 4 * q),
-                             "f"(__uint_as_float(r[4 * q])), "f"(__uint_as_float(r[4 * q + 1])),
-                             "f"(__uint_as_float(r[4 * q + 2])), "f"(__uint_as_float(r[4 * q + 3]))
-                             : "memory");
-              }
-            }
-          } else {
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) {
-                if (EPI == EPI_STORE_F32) crow[j] = __uint_as_float(r[j]);
-                else atomicAdd(crow + j, __uint_as_float(r[j]));
-              }
-          }
-        }
+        store_chunk<EPI>(r, row, n_idx * BLOCK_N + c * 32, p);
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;

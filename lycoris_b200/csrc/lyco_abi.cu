@@ -4,11 +4,13 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
 
 #include "../../include/lyco_b200.h"
+#include "gemm_pair_sm100.cuh"
 #include "gemm_sm100.cuh"
 #include "weight_kernels.cuh"
 
@@ -111,6 +113,48 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const lyco::GemmPa
   return 0;
 }
 
+template <int BN, bool A_MN, bool B_MN, int EPI>
+int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, const lyco::GemmParams& p, int grid,
+                     cudaStream_t stream) {
+  auto kern = lyco::gemm_pair_sm100_kernel<BN, A_MN, B_MN, EPI>;
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!configured[dev & 63]) {
+    LYCO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   lyco::PairCfg<BN>::SMEM_BYTES));
+    configured[dev & 63] = true;
+  }
+  kern<<<grid, lyco::GEMM_THREADS, lyco::PairCfg<BN>::SMEM_BYTES, stream>>>(ta, tb, p);
+  LYCO_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+template <int BN>
+int dispatch_gemm_pair(bool a_mn, bool b_mn, int epi, const CUtensorMap& ta, const CUtensorMap& tb,
+                       const lyco::GemmParams& p, int grid, cudaStream_t s) {
+  using namespace lyco;
+  if (!a_mn && !b_mn) {
+    if (epi == EPI_STORE16) return launch_gemm_pair<BN, false, false, EPI_STORE16>(ta, tb, p, grid, s);
+    if (epi == EPI_STORE_F32) return launch_gemm_pair<BN, false, false, EPI_STORE_F32>(ta, tb, p, grid, s);
+    return launch_gemm_pair<BN, false, false, EPI_ATOMIC_F32>(ta, tb, p, grid, s);
+  }
+  if (!a_mn && b_mn) {
+    if (epi == EPI_STORE16) return launch_gemm_pair<BN, false, true, EPI_STORE16>(ta, tb, p, grid, s);
+    if (epi == EPI_STORE_F32) return launch_gemm_pair<BN, false, true, EPI_STORE_F32>(ta, tb, p, grid, s);
+    return launch_gemm_pair<BN, false, true, EPI_ATOMIC_F32>(ta, tb, p, grid, s);
+  }
+  if (a_mn && b_mn) {
+    if (epi == EPI_STORE16) return launch_gemm_pair<BN, true, true, EPI_STORE16>(ta, tb, p, grid, s);
+    if (epi == EPI_STORE_F32) return launch_gemm_pair<BN, true, true, EPI_STORE_F32>(ta, tb, p, grid, s);
+    return launch_gemm_pair<BN, true, true, EPI_ATOMIC_F32>(ta, tb, p, grid, s);
+  }
+  if (epi == EPI_STORE16) return launch_gemm_pair<BN, true, false, EPI_STORE16>(ta, tb, p, grid, s);
+  if (epi == EPI_STORE_F32) return launch_gemm_pair<BN, true, false, EPI_STORE_F32>(ta, tb, p, grid, s);
+  return launch_gemm_pair<BN, true, false, EPI_ATOMIC_F32>(ta, tb, p, grid, s);
+}
+
 template <int BN>
 int dispatch_gemm(bool a_mn, bool b_mn, int epi, const CUtensorMap& ta, const CUtensorMap& tb,
                   const lyco::GemmParams& p, int grid, cudaStream_t s) {
@@ -137,21 +181,47 @@ int dispatch_gemm(bool a_mn, bool b_mn, int epi, const CUtensorMap& ta, const CU
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
-// Relative cost of one 128 x bn tile step: tensor-pipe time ~ bn, L2->SM feed ~ (128 + bn).
-inline double tile_cost(int bn) {
-  const double mma = bn, feed = 0.85 * (128 + bn);
+// Relative cost of one k-block of a tile.  Tensor-pipe time ~ bn for both variants (a CTA pair runs a
+// 256-row tile at twice the rate); the L2 -> SM feed per CTA is ~(128 + bn) rows for a single CTA and
+// ~(128 + bn/2) for a pair member.  0.85 = measured feed/MMA balance of the 1-CTA kernel at 128x256.
+struct TileChoice {
+  bool pair;
+  int bn;
+};
+
+inline double tile_cost(bool pair, int bn) {
+  const double mma = bn, feed = 0.85 * (128 + (pair ? bn / 2 : bn));
   return mma > feed ? mma : feed;
 }
 
-int pick_block_n(int M, int N, int sms, int splits_hint) {
-  int best = 64;
+inline int force_choice(TileChoice* c) {
+  // LYCO_GEMM_FORCE=pair256|pair128|single256|single128|single64 (experiments / tests)
+  static const char* env = getenv("LYCO_GEMM_FORCE");
+  if (!env || !*env) return 0;
+  if (!strncmp(env, "pair", 4)) { c->pair = true; c->bn = atoi(env + 4); return c->bn == 256 || c->bn == 128; }
+  if (!strncmp(env, "single", 6)) { c->pair = false; c->bn = atoi(env + 6); return c->bn == 256 || c->bn == 128 || c->bn == 64; }
+  return 0;
+}
+
+inline bool pair_enabled() {
+  // CTA-pair kernels are the default; LYCO_GEMM_PAIR=0 restricts the choice to single-CTA tiles
+  static const bool on = []() { const char* e = getenv("LYCO_GEMM_PAIR"); return !(e && *e == '0'); }();
+  return on;
+}
+
+TileChoice pick_tile(int M, int N, int sms, int splits_hint) {
+  TileChoice best{false, 64};
+  if (force_choice(&best)) return best;
   double best_cost = 1e30;
-  const int cands[3] = {256, 128, 64};
-  for (int bn : cands) {
-    const long tiles = static_cast<long>(cdiv(M, 128)) * cdiv(N, bn) * (splits_hint > 0 ? splits_hint : 1);
-    const long waves = (tiles + sms - 1) / sms;
-    const double cost = waves * tile_cost(bn);
-    if (cost < best_cost * 0.999) { best_cost = cost; best = bn; }
+  const TileChoice cands[5] = {{true, 256}, {true, 128}, {false, 256}, {false, 128}, {false, 64}};
+  const int sp = splits_hint > 0 ? splits_hint : 1;
+  for (const TileChoice& c : cands) {
+    if (c.pair && (M <= 128 || !pair_enabled())) continue;
+    const long tiles = static_cast<long>(cdiv(M, c.pair ? 256 : 128)) * cdiv(N, c.bn) * sp;
+    const long slots = c.pair ? sms / 2 : sms;
+    const long waves = (tiles + slots - 1) / slots;
+    const double cost = waves * tile_cost(c.pair, c.bn);
+    if (cost < best_cost * 0.999) { best_cost = cost; best = c; }
   }
   return best;
 }
@@ -237,21 +307,24 @@ int lyco_gemm(const void* A, int a_mn_major, int64_t lda, const void* B, int b_m
 
   const int k_blocks = cdiv(K, lyco::GEMM_BLOCK_K);
   int splits = 1;
-  const int m_tiles = cdiv(M, lyco::GEMM_BLOCK_M);
-  int bn = pick_block_n(M, N, di.sms, 1);
+  TileChoice tc = pick_tile(M, N, di.sms, 1);
   if (c_dtype == LYCO_F32) {
-    // wgrad-like: few output tiles, long reduction -> split the reduction across CTAs
-    bn = N >= 256 ? 256 : (N >= 128 ? 128 : 64);
-    const long tiles = static_cast<long>(m_tiles) * cdiv(N, bn);
-    splits = split_k > 0 ? split_k : pick_splits(tiles, k_blocks, di.sms);
+    // wgrad-like: few output tiles, long reduction -> largest tile, split the reduction across CTAs
+    TileChoice forced;
+    if (force_choice(&forced)) tc = forced;
+    else { tc.pair = M > 128 && pair_enabled(); tc.bn = N >= 256 ? 256 : (N >= 128 ? 128 : 64); if (tc.bn == 64) tc.pair = false; }
+    const long tiles = static_cast<long>(cdiv(M, tc.pair ? 256 : 128)) * cdiv(N, tc.bn);
+    splits = split_k > 0 ? split_k : pick_splits(tiles, k_blocks, tc.pair ? di.sms / 2 : di.sms);
     if (splits > k_blocks) splits = k_blocks;
   }
+  const int bn = tc.bn;
+  const int m_tiles = cdiv(M, tc.pair ? lyco::PAIR_BLOCK_M : lyco::GEMM_BLOCK_M);
   const int n_tiles = cdiv(N, bn);
 
   CUtensorMap ta, tb;
   if (!a_mn_major) { if (make_tmap(&ta, A, K, M, lda, 64, 128)) return 1; }
   else             { if (make_tmap(&ta, A, M, K, lda, 64, 64)) return 1; }
-  if (!b_mn_major) { if (make_tmap(&tb, B, K, N, ldb, 64, bn)) return 1; }
+  if (!b_mn_major) { if (make_tmap(&tb, B, K, N, ldb, 64, tc.pair ? bn / 2 : bn)) return 1; }
   else             { if (make_tmap(&tb, B, N, K, ldb, 64, 64)) return 1; }
 
   lyco::GemmParams p;
@@ -269,8 +342,14 @@ int lyco_gemm(const void* A, int a_mn_major, int64_t lda, const void* B, int b_m
     }
   }
   const long total = static_cast<long>(m_tiles) * n_tiles * splits;
-  const int grid = static_cast<int>(total < di.sms ? total : di.sms);
   const bool a_mn = a_mn_major != 0, b_mn = b_mn_major != 0;
+  if (tc.pair) {
+    const long slots = di.sms / 2;
+    const int grid = 2 * static_cast<int>(total < slots ? total : slots);
+    if (bn == 256) return dispatch_gemm_pair<256>(a_mn, b_mn, epi, ta, tb, p, grid, stream);
+    return dispatch_gemm_pair<128>(a_mn, b_mn, epi, ta, tb, p, grid, stream);
+  }
+  const int grid = static_cast<int>(total < di.sms ? total : di.sms);
   if (bn == 256) return dispatch_gemm<256>(a_mn, b_mn, epi, ta, tb, p, grid, stream);
   if (bn == 128) return dispatch_gemm<128>(a_mn, b_mn, epi, ta, tb, p, grid, stream);
   return dispatch_gemm<64>(a_mn, b_mn, epi, ta, tb, p, grid, stream);

@@ -29,6 +29,8 @@ def _setup(algo_kwargs, preset="full", dim=4, alpha=2, channels_last=True, regim
         net = kohya.LycorisNetworkKohya(None, unet, 1.0, dim, dim, alpha, alpha, **algo_kwargs)
     else:
         net = kohya.create_network(1.0, dim, alpha, None, None, unet, preset=preset, **algo_kwargs)
+    for lora in net.loras:  # register the adapters so .cuda()/.to() reach them (apply_to does this too)
+        net.add_module(lora.lora_name, lora)
     net.cuda()
     if regime == "bf16":
         net.to(torch.bfloat16)
@@ -68,7 +70,11 @@ CASES = [
     ("loha", dict(algo="loha", conv_dim=4, conv_alpha=1), "full", 8, "autocast"),
     ("locon_bf16", dict(algo="locon", conv_dim=4, conv_alpha=1), "full", 8, "bf16"),
     ("lokr_bf16", dict(algo="lokr", factor=8), "attn-mlp", 100000, "bf16"),
-    ("ia3", dict(algo="ia3"), "ia3", 4, "autocast"),
+    # the built-in "ia3" preset lists bare names ("to_k", ...) that re.match only finds at the START of a
+    # module path, so on diffusers-style paths it selects nothing (same in the reference); use regexes
+    ("ia3", dict(network_module="ia3"), {
+        "enable_conv": False, "unet_target_module": [], "unet_target_name": [r".*to_k$", r".*to_v$", r".*ff\.net\.2$"],
+        "name_algo_map": {r".*ff\.net\.2$": {"train_on_input": True}}, "module_algo_map": {}}, 4, "autocast"),
     ("dylora", dict(algo="dylora", block_size=2, conv_dim=4), "full", 8, "autocast"),
 ]
 
@@ -79,8 +85,6 @@ def test_network_fwd_bwd_matches_oracle_network(name, kw, preset, dim, regime):
     assert len(net.loras) > 0
     # reference-equivalent path
     undo = oracle_patch_network(net)
-    for lora in net.loras:
-        net.add_module(lora.lora_name, lora)
     ref_loss, ref_out, ref_dx, ref_g = _run(unet, net, st, regime)
     undo()
     # engine path
@@ -140,6 +144,9 @@ def test_mixed_algo_preset_runs_and_trains():
 def test_cuda_graph_capture_of_a_step():
     """The engine launches only on the current stream with no host sync: a whole fwd+bwd step is
     graph-capturable and replays to the same loss."""
+    # all autograd use of the parameters must happen off the legacy default stream, or their
+    # AccumulateGrad nodes get bound to it and the capture is invalidated
+    torch.cuda.set_stream(torch.cuda.Stream())
     unet, net, st = _setup(dict(algo="lokr", factor=8), "full", 100000, 1, True, "autocast")
     net.apply_to(None, unet, False, True)
 
@@ -154,15 +161,12 @@ def test_cuda_graph_capture_of_a_step():
 
     for _ in range(3):
         eager = float(step())
-    s = torch.cuda.Stream()
-    s.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(s):
-        step()
-    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
         static_loss = step()
     g.replay()
     torch.cuda.synchronize()
     net.restore()
+    torch.cuda.set_stream(torch.cuda.default_stream())
     assert abs(float(static_loss) - eager) <= 1e-3 * abs(eager) + 1e-6

@@ -10,7 +10,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def case_gemm(M, N, K, a_mn, b_mn, out, bias, split_k=0, dtype="bf16"):
+def case_gemm(M, N, K, a_mn, b_mn, out, bias, split_k=0, dtype="bf16", force=None):
+    if force:
+        os.environ["LYCO_GEMM_FORCE"] = force
     import torch
     from lycoris_b200.engine import kernels as k
 
@@ -151,6 +153,23 @@ CASES += [
     ("gemm", dict(M=32768, N=640, K=640, a_mn=False, b_mn=False, out="16", bias=True)),
     ("gemm", dict(M=616, N=1280, K=2048, a_mn=False, b_mn=False, out="16", bias=False)),
     ("gemm", dict(M=1024, N=512, K=512, a_mn=False, b_mn=False, out="16", bias=True, dtype="f16")),
+    # CTA-pair (cta_group::2) variants
+    ("gemm", dict(M=512, N=512, K=256, a_mn=False, b_mn=False, out="16", bias=True, force="pair256")),
+    ("gemm", dict(M=512, N=512, K=256, a_mn=False, b_mn=False, out="16", bias=True, force="pair128")),
+    ("gemm", dict(M=1000, N=328, K=200, a_mn=False, b_mn=False, out="16", bias=False, force="pair256")),
+    ("gemm", dict(M=512, N=512, K=256, a_mn=False, b_mn=True, out="16", bias=False, force="pair256")),
+    ("gemm", dict(M=512, N=512, K=256, a_mn=True, b_mn=True, out="f32", bias=False, split_k=1, force="pair256")),
+    ("gemm", dict(M=512, N=512, K=256, a_mn=True, b_mn=True, out="f32", bias=False, split_k=3, force="pair128")),
+    ("gemm", dict(M=8192, N=1280, K=1280, a_mn=False, b_mn=False, out="16", bias=True, force="pair256")),
+    ("gemm", dict(M=8192, N=1280, K=1280, a_mn=False, b_mn=False, out="16", bias=True, force="pair128")),
+    ("gemm", dict(M=8192, N=10240, K=1280, a_mn=False, b_mn=False, out="16", bias=True, force="pair256")),
+    ("gemm", dict(M=8192, N=1280, K=5120, a_mn=False, b_mn=False, out="16", bias=True, force="pair256")),
+    ("gemm", dict(M=8192, N=1280, K=1280, a_mn=False, b_mn=True, out="16", bias=False, force="pair256")),
+    ("gemm", dict(M=1280, N=1280, K=8192, a_mn=True, b_mn=True, out="f32", bias=False, split_k=0, force="pair256")),
+    ("gemm", dict(M=32768, N=640, K=640, a_mn=False, b_mn=False, out="16", bias=True, force="pair256")),
+    ("gemm", dict(M=32768, N=640, K=640, a_mn=False, b_mn=False, out="16", bias=True, force="pair128")),
+    ("gemm", dict(M=8192, N=10240, K=1280, a_mn=False, b_mn=False, out="16", bias=True)),
+    ("gemm", dict(M=8192, N=1280, K=1280, a_mn=False, b_mn=False, out="16", bias=True)),
     ("weight", dict(algo="locon", N=1280, K=1280, r=16)),
     ("weight", dict(algo="locon", N=320, K=2880, r=8, fdt="bf16")),
     ("weight", dict(algo="loha", N=1280, K=1280, r=32)),
