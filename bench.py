@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--sample-size", type=int, default=0, help="latent side (default: the model's)")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-table", default="", help="write a per-kernel CUDA-time table of one eager step here")
+    ap.add_argument("--nvtx-step", action="store_true", help="wrap ONE extra eager step in an NVTX range 'lyco_step' (for ncu --nvtx-include)")
     return ap.parse_args()
 
 
@@ -125,7 +127,9 @@ def build_engine_workload(args, device):
 
     cfg = model_cfg(args.model)
     torch.manual_seed(0)
-    unet = UNetSkeleton(cfg).to(device=device, dtype=torch.bfloat16).to(memory_format=torch.channels_last)
+    # activations travel channels_last (NHWC) — what the TMA-im2col producer and cuDNN both want; the
+    # frozen filters stay in PyTorch's [O, C, kh, kw] layout, which is the layout the reference flattens
+    unet = UNetSkeleton(cfg).to(device=device, dtype=torch.bfloat16)
     unet.requires_grad_(False)
     unet.train()
     na = network_args(args.algo)
@@ -284,6 +288,31 @@ def run_engine(args):
     e1.record()
     torch.cuda.synchronize()
     eager_ms = e0.elapsed_time(e1)
+
+    if args.kernel_table and rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            step()
+            torch.cuda.synchronize()
+        agg = {}
+        for ev in prof.events():
+            if ev.device_type is not None and str(ev.device_type).endswith("CUDA") and ev.device_time_total > 0:
+                name = ev.name.split("<")[0][:90]
+                a = agg.setdefault(name, [0, 0.0])
+                a[0] += 1
+                a[1] += ev.device_time_total
+        tot = sum(v[1] for v in agg.values())
+        with open(args.kernel_table, "w") as fh:
+            fh.write(f"one eager step, CUDA kernels by total device time (us); sum = {tot / 1e3:.2f} ms\n")
+            for name, (cnt, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                fh.write(f"{t / 1e3:10.3f} ms {100 * t / tot:5.1f}% {cnt:6d}  {name}\n")
+    if args.nvtx_step:
+        torch.cuda.synchronize()
+        torch.cuda.nvtx.range_push("lyco_step")
+        step()
+        torch.cuda.synchronize()
+        torch.cuda.nvtx.range_pop()
 
     peaks = {}
     try:

@@ -88,6 +88,34 @@ int lyco_gemm(const void* A, int a_mn_major, int64_t lda,
               int ab_dtype, int split_k, void* stream);
 
 /* ------------------------------------------------------------------------- */
+/* implicit-GEMM convolution (tcgen05 + TMA im2col)                           */
+/* ------------------------------------------------------------------------- */
+
+/*
+ * Y[n,p,q,o] = sum_{r,s,c} X[n, p*stride - pad_h + r, q*stride - pad_w + s, c] * Wk[o, r, s, c]  (+ bias[o])
+ *
+ * X is NHWC (torch channels_last storage) [Nb, H, W, C]; Wk is the merged filter re-laid as
+ * [O, R, S, C]; Y is NHWC [Nb, P, Q, O] with P = (H + 2*pad_h - R)/stride + 1 (same for Q).
+ * Needs C % 64 == 0 and O % 8 == 0, dilation 1, groups 1.
+ * The input-gradient (stride 1) is the same call on dY with the flipped/transposed filter
+ * [C, R, S, O] and pad' = R-1-pad.
+ * Replaces F.conv2d on base and delta weights lycoris/modules/locon.py:317,331 (conv branch of
+ * LycorisBaseModule, base.py:110-124) and autograd's dgrad for both.
+ */
+int lyco_conv2d_fprop(const void* X, const void* Wk, void* Y, const void* bias, int bias_dtype,
+                      int Nb, int H, int W, int C, int O, int R, int S, int pad_h, int pad_w,
+                      int stride, int dtype, void* stream);
+
+/*
+ * dW[o, r, s, c] (fp32, [O, R*S*C]) = sum_{n,p,q} dY[n,p,q,o] * X[n, p*stride - pad_h + r, q*stride - pad_w + s, c]
+ * dY is NHWC [Nb, P, Q, O].  Needs C % 64 == 0, O % 8 == 0.  split_k as in lyco_gemm.
+ * Replaces autograd's weight-gradient of the delta convolution (d(delta_weight), locon.py:331).
+ */
+int lyco_conv2d_wgrad(const void* X, const void* dY, float* dW, int Nb, int H, int W, int C, int O,
+                      int R, int S, int pad_h, int pad_w, int stride, int dtype, int split_k,
+                      void* stream);
+
+/* ------------------------------------------------------------------------- */
 /* weight-side kernels (HBM-bound)                                            */
 /* ------------------------------------------------------------------------- */
 

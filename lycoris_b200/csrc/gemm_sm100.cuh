@@ -70,9 +70,11 @@ __device__ __forceinline__ uint32_t pack16(float a, float b, int fmt) {
 
 // Epilogue for one 32-column chunk of one accumulator row held in registers (fp32 bit patterns).
 template <int EPI>
-__device__ __forceinline__ void store_chunk(const uint32_t (&r)[32], int row, int col0, const GemmParams& p) {
-  if (row >= p.M || col0 >= p.N) return;
-  const bool full = (col0 + 32 <= p.N);
+__device__ __forceinline__ void store_chunk(const uint32_t (&r)[32], int row, int col0, const GemmParams& p,
+                                            int col_limit = -1) {
+  const int N = col_limit < 0 ? p.N : col_limit;  // first column this tile must not write
+  if (row >= p.M || col0 >= N) return;
+  const bool full = (col0 + 32 <= N);
   if (EPI == EPI_STORE16) {
     float v[32];
 #pragma unroll
@@ -106,7 +108,7 @@ __device__ __forceinline__ void store_chunk(const uint32_t (&r)[32], int row, in
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (col0 + j < p.N) v[j] += load_scalar(p.bias, p.bias_dtype, col0 + j);
+          if (col0 + j < N) v[j] += load_scalar(p.bias, p.bias_dtype, col0 + j);
       }
     }
     uint16_t* crow = reinterpret_cast<uint16_t*>(p.C) + static_cast<int64_t>(row) * p.ldc + col0;
@@ -123,7 +125,7 @@ __device__ __forceinline__ void store_chunk(const uint32_t (&r)[32], int row, in
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (col0 + j < p.N) crow[j] = static_cast<uint16_t>(pack16(v[j], 0.f, p.fmt) & 0xFFFF);
+        if (col0 + j < N) crow[j] = static_cast<uint16_t>(pack16(v[j], 0.f, p.fmt) & 0xFFFF);
     }
   } else {
     float* crow = reinterpret_cast<float*>(p.C) + static_cast<int64_t>(row) * p.ldc + col0;
@@ -144,7 +146,7 @@ __device__ __forceinline__ void store_chunk(const uint32_t (&r)[32], int row, in
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (col0 + j < p.N) {
+        if (col0 + j < N) {
           if (EPI == EPI_STORE_F32) crow[j] = __uint_as_float(r[j]);
           else atomicAdd(crow + j, __uint_as_float(r[j]));
         }

@@ -10,6 +10,7 @@
 #include <atomic>
 
 #include "../../include/lyco_b200.h"
+#include "conv_sm100.cuh"
 #include "gemm_pair_sm100.cuh"
 #include "gemm_sm100.cuh"
 #include "weight_kernels.cuh"
@@ -92,6 +93,62 @@ int make_tmap(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, 
     return fail("cuTensorMapEncodeTiled failed (%d): base=%p inner=%llu outer=%llu ld=%llu box=%ux%u",
                 static_cast<int>(r), base, (unsigned long long)inner, (unsigned long long)outer,
                 (unsigned long long)ld_elems, box_inner, box_outer);
+  return 0;
+}
+
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeIm2colFn encode_im2col() {
+  static EncodeIm2colFn fn = []() -> EncodeIm2colFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<EncodeIm2colFn>(p);
+  }();
+  return fn;
+}
+
+// im2col tensor map over an NHWC tensor: boxes of `pixels` output positions x 64 channels, 128B swizzle
+int make_tmap_im2col(CUtensorMap* m, const void* base, int Nb, int H, int W, int C, int R, int S, int pad_h,
+                     int pad_w, int stride, uint32_t pixels) {
+  EncodeIm2colFn enc = encode_im2col();
+  if (!enc) return fail("cuTensorMapEncodeIm2col is not available from the driver");
+  cuuint64_t gdim[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                        static_cast<cuuint64_t>(Nb)};
+  cuuint64_t gstr[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(W) * C * 2,
+                        static_cast<cuuint64_t>(H) * W * C * 2};
+  int lower[2] = {-pad_w, -pad_h};                      // {W, H} order (as CUTLASS passes them)
+  int upper[2] = {pad_w - (S - 1), pad_h - (R - 1)};
+  cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(stride), static_cast<cuuint32_t>(stride), 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, lower, upper, 64,
+                   pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail("cuTensorMapEncodeIm2col failed (%d): N=%d H=%d W=%d C=%d R=%d S=%d pad=%d,%d stride=%d pixels=%u",
+                static_cast<int>(r), Nb, H, W, C, R, S, pad_h, pad_w, stride, pixels);
+  return 0;
+}
+
+template <int BN, int MODE, int EPI>
+int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const lyco::ConvParams& cp, int grid,
+                cudaStream_t stream) {
+  auto kern = lyco::conv_sm100_kernel<BN, MODE, EPI>;
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!configured[dev & 63]) {
+    LYCO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   lyco::GemmCfg<BN>::SMEM_BYTES));
+    configured[dev & 63] = true;
+  }
+  kern<<<grid, lyco::GEMM_THREADS, lyco::GemmCfg<BN>::SMEM_BYTES, stream>>>(ta, tb, cp);
+  LYCO_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }
 
@@ -355,6 +412,102 @@ int lyco_gemm(const void* A, int a_mn_major, int64_t lda, const void* B, int b_m
   return dispatch_gemm<64>(a_mn, b_mn, epi, ta, tb, p, grid, stream);
 }
 
+int lyco_conv2d_fprop(const void* X, const void* Wk, void* Y, const void* bias, int bias_dtype, int Nb, int H,
+                      int W, int C, int O, int R, int S, int pad_h, int pad_w, int stride, int dtype,
+                      void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!X || !Wk || !Y) return fail("lyco_conv2d_fprop: null operand");
+  if (dtype != LYCO_BF16 && dtype != LYCO_F16) return fail("lyco_conv2d_fprop: operands must be bf16/f16");
+  if (C % 64 || O % 8) return fail("lyco_conv2d_fprop: needs C %% 64 == 0 and O %% 8 == 0 (C=%d O=%d)", C, O);
+  if (stride < 1 || stride > 8 || R < 1 || S < 1) return fail("lyco_conv2d_fprop: bad geometry");
+  if ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Wk) | reinterpret_cast<uintptr_t>(Y)) & 15)
+    return fail("lyco_conv2d_fprop: pointers must be 16-byte aligned");
+  const int P = (H + 2 * pad_h - R) / stride + 1, Q = (W + 2 * pad_w - S) / stride + 1;
+  if (P <= 0 || Q <= 0) return fail("lyco_conv2d_fprop: empty output");
+  DeviceInfo di;
+  if (device_info(&di)) return 1;
+  const int64_t M64 = static_cast<int64_t>(Nb) * P * Q;
+  if (M64 > (1ll << 30)) return fail("lyco_conv2d_fprop: too many output pixels");
+  const int M = static_cast<int>(M64), K = R * S * C;
+  TileChoice tc{false, 64};
+  {
+    double best = 1e30;
+    const int cands[3] = {256, 128, 64};
+    for (int bn : cands) {
+      const long tiles = static_cast<long>(cdiv(M, 128)) * cdiv(O, bn);
+      const long waves = (tiles + di.sms - 1) / di.sms;
+      const double cost = waves * tile_cost(false, bn);
+      if (cost < best * 0.999) { best = cost; tc.bn = bn; }
+    }
+  }
+  const int bn = tc.bn;
+  CUtensorMap ta, tb;
+  if (make_tmap_im2col(&ta, X, Nb, H, W, C, R, S, pad_h, pad_w, stride, 128)) return 1;
+  if (make_tmap(&tb, Wk, K, O, K, 64, bn)) return 1;
+  lyco::ConvParams cp;
+  cp.g.C = Y; cp.g.bias = bias; cp.g.ldc = O; cp.g.M = M; cp.g.N = O; cp.g.K = K;
+  cp.g.m_tiles = cdiv(M, 128); cp.g.n_tiles = cdiv(O, bn); cp.g.splits = 1; cp.g.k_blocks = R * S * (C / 64);
+  cp.g.fmt = (dtype == LYCO_BF16) ? 1 : 0; cp.g.bias_dtype = bias_dtype;
+  cp.PQ = P * Q; cp.Q = Q; cp.C = C; cp.CB = C / 64; cp.S = S; cp.stride = stride;
+  cp.low_w = -pad_w; cp.low_h = -pad_h; cp.tiles_per_tap = 1;
+  const long total = static_cast<long>(cp.g.m_tiles) * cp.g.n_tiles;
+  const int grid = static_cast<int>(total < di.sms ? total : di.sms);
+  if (bn == 256) return launch_conv<256, lyco::MODE_FPROP, lyco::EPI_STORE16>(ta, tb, cp, grid, stream);
+  if (bn == 128) return launch_conv<128, lyco::MODE_FPROP, lyco::EPI_STORE16>(ta, tb, cp, grid, stream);
+  return launch_conv<64, lyco::MODE_FPROP, lyco::EPI_STORE16>(ta, tb, cp, grid, stream);
+}
+
+int lyco_conv2d_wgrad(const void* X, const void* dY, float* dW, int Nb, int H, int W, int C, int O, int R, int S,
+                      int pad_h, int pad_w, int stride, int dtype, int split_k, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!X || !dY || !dW) return fail("lyco_conv2d_wgrad: null operand");
+  if (dtype != LYCO_BF16 && dtype != LYCO_F16) return fail("lyco_conv2d_wgrad: operands must be bf16/f16");
+  if (C % 64 || O % 8) return fail("lyco_conv2d_wgrad: needs C %% 64 == 0 and O %% 8 == 0 (C=%d O=%d)", C, O);
+  const int P = (H + 2 * pad_h - R) / stride + 1, Q = (W + 2 * pad_w - S) / stride + 1;
+  if (P <= 0 || Q <= 0) return fail("lyco_conv2d_wgrad: empty output");
+  DeviceInfo di;
+  if (device_info(&di)) return 1;
+  const int64_t M64 = static_cast<int64_t>(Nb) * P * Q;
+  if (M64 > (1ll << 30)) return fail("lyco_conv2d_wgrad: too many output pixels");
+  const int Mpix = static_cast<int>(M64);
+  // N tile: the widest of 256/128/64 that wastes the least padding inside one filter tap
+  int bn = 64;
+  double best = 1e30;
+  const int cands[3] = {256, 128, 64};
+  for (int c : cands) {
+    const double waste = static_cast<double>(cdiv(C, c) * c) / C;  // >= 1
+    const double cost = waste * tile_cost(false, c) / c;
+    if (cost < best * 0.999) { best = cost; bn = c; }
+  }
+  const int tiles_per_tap = cdiv(C, bn);
+  const int taps = R * S;
+  const int k_blocks = cdiv(Mpix, 64);
+  const long tiles = static_cast<long>(cdiv(O, 128)) * taps * tiles_per_tap;
+  int splits = split_k > 0 ? split_k : pick_splits(tiles, k_blocks, di.sms);
+  if (splits > k_blocks) splits = k_blocks;
+  CUtensorMap ta, tb;
+  if (make_tmap(&ta, dY, O, Mpix, O, 64, 64)) return 1;  // dY [Mpix, O] consumed MN-major
+  if (make_tmap_im2col(&tb, X, Nb, H, W, C, R, S, pad_h, pad_w, stride, 64)) return 1;
+  lyco::ConvParams cp;
+  const int ldw = taps * C;
+  cp.g.C = dW; cp.g.bias = nullptr; cp.g.ldc = ldw; cp.g.M = O; cp.g.N = ldw; cp.g.K = Mpix;
+  cp.g.m_tiles = cdiv(O, 128); cp.g.n_tiles = taps * tiles_per_tap; cp.g.splits = splits; cp.g.k_blocks = k_blocks;
+  cp.g.fmt = (dtype == LYCO_BF16) ? 1 : 0; cp.g.bias_dtype = 0;
+  cp.PQ = P * Q; cp.Q = Q; cp.C = C; cp.CB = C / 64; cp.S = S; cp.stride = stride;
+  cp.low_w = -pad_w; cp.low_h = -pad_h; cp.tiles_per_tap = tiles_per_tap;
+  if (splits > 1) LYCO_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * static_cast<size_t>(O) * ldw, stream));
+  const long total = tiles * splits;
+  const int grid = static_cast<int>(total < di.sms ? total : di.sms);
+  if (splits > 1) {
+    if (bn == 256) return launch_conv<256, lyco::MODE_WGRAD, lyco::EPI_ATOMIC_F32>(ta, tb, cp, grid, stream);
+    if (bn == 128) return launch_conv<128, lyco::MODE_WGRAD, lyco::EPI_ATOMIC_F32>(ta, tb, cp, grid, stream);
+    return launch_conv<64, lyco::MODE_WGRAD, lyco::EPI_ATOMIC_F32>(ta, tb, cp, grid, stream);
+  }
+  if (bn == 256) return launch_conv<256, lyco::MODE_WGRAD, lyco::EPI_STORE_F32>(ta, tb, cp, grid, stream);
+  if (bn == 128) return launch_conv<128, lyco::MODE_WGRAD, lyco::EPI_STORE_F32>(ta, tb, cp, grid, stream);
+  return launch_conv<64, lyco::MODE_WGRAD, lyco::EPI_STORE_F32>(ta, tb, cp, grid, stream);
+}
+
 int lyco_merge_weight(const lyco_delta_desc_t* d, const void* W, void* W_out, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (check_desc(d)) return 1;
@@ -426,13 +579,20 @@ int lyco_factor_grads(const lyco_delta_desc_t* d, const float* dW, const void* W
     case LYCO_ALGO_LOKR: {
       if (!g0 || !g1) return fail("lyco_factor_grads: missing gradient buffers");
       const size_t n_w1 = static_cast<size_t>(d->up) * d->uq;
-      LYCO_CUDA(cudaMemsetAsync(g0, 0, sizeof(float) * n_w1, stream));
       const int64_t plane = static_cast<int64_t>(d->vp) * d->vq;
-      const int grid = static_cast<int>((plane + 255) / 256);
-      if (n_w1 * sizeof(float) <= 32 * 1024)
-        lyco::grad_lokr_kernel<true><<<grid, 256, n_w1 * sizeof(float), stream>>>(*d, dW, g0, g1);
-      else
-        lyco::grad_lokr_kernel<false><<<grid, 256, 0, stream>>>(*d, dW, g0, g1);
+      LYCO_CUDA(cudaMemsetAsync(g0, 0, sizeof(float) * n_w1, stream));
+      LYCO_CUDA(cudaMemsetAsync(g1, 0, sizeof(float) * static_cast<size_t>(plane), stream));
+      if (d->up > 65535) return fail("lyco_factor_grads: lokr up=%d too large", d->up);
+      const bool vec4 = (d->vq % 4 == 0) && (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(dW) & 15) == 0);
+      const size_t smem = sizeof(float) * static_cast<size_t>(d->uq);
+      if (smem > 40 * 1024) return fail("lyco_factor_grads: lokr uq=%d too large", d->uq);
+      if (vec4) {
+        dim3 grid(static_cast<unsigned>((plane / 4 + 255) / 256), static_cast<unsigned>(d->up));
+        lyco::grad_lokr_kernel<4><<<grid, 256, smem, stream>>>(*d, dW, g0, g1);
+      } else {
+        dim3 grid(static_cast<unsigned>((plane + 255) / 256), static_cast<unsigned>(d->up));
+        lyco::grad_lokr_kernel<1><<<grid, 256, smem, stream>>>(*d, dW, g0, g1);
+      }
       break;
     }
     case LYCO_ALGO_IA3: {

@@ -331,46 +331,63 @@ __global__ void __launch_bounds__(256) grad_lowrank_kernel(lyco_delta_desc_t d, 
 
 // LoKr: g_w1[pu,u] = sum_{pv,v} dW[pu*vp+pv, u*vq+v] * w2[pv,v]
 //       g_w2[pv,v] = sum_{pu,u} dW[...]              * w1[pu,u]
-// One CTA owns a strip of the (pv, v) plane and walks all (pu, u) blocks, so g_w2 needs no
-// atomics; g_w1 takes one atomic per warp per block.
-template <bool SMEM_W1>
+// grid = (plane tiles, up): a CTA owns VEC*256 consecutive (pv,v) plane elements of ONE w1 row pu and walks
+// the uq blocks of that row (short loop, 16-byte loads); g_w1 partials are staged in shared memory
+// (one global atomic per entry per CTA), g_w2 takes `up` atomics per element (g_w2 is zero-filled first).
+template <int VEC>
 __global__ void __launch_bounds__(256) grad_lokr_kernel(lyco_delta_desc_t d, const float* __restrict__ dW,
                                                         float* g_w1, float* g_w2) {
-  extern __shared__ float s_w1[];  // [up*uq] partial sums of g_w1 for this CTA (SMEM_W1 only)
+  extern __shared__ float s_w1[];  // [uq]
   const int K = d.in_dim;
-  const int n_w1 = d.up * d.uq;
-  if (SMEM_W1) {
-    for (int i = threadIdx.x; i < n_w1; i += blockDim.x) s_w1[i] = 0.f;
-    __syncthreads();
-  }
+  const int pu = blockIdx.y;
+  for (int i = threadIdx.x; i < d.uq; i += blockDim.x) s_w1[i] = 0.f;
+  __syncthreads();
   const int fround = d.pre_round ? d.pre_dtype : LYCO_F32;
   const float gscale = d.m_pre * d.m_post1 * d.m_post2;
   const int64_t plane = static_cast<int64_t>(d.vp) * d.vq;
-  const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const bool live = e < plane;
-  const int pv = live ? static_cast<int>(e / d.vq) : 0;
-  const int v = live ? static_cast<int>(e % d.vq) : 0;
-  const float b = live ? rnd(ld_f(d.f1, d.f_dtype, e), fround) : 0.f;
-  const int lane = threadIdx.x & 31;
-  float acc = 0.f;
-  for (int pu = 0; pu < d.up; ++pu) {
-    for (int u = 0; u < d.uq; ++u) {
-      float g = 0.f;
-      if (live)
-        g = __ldg(&dW[static_cast<int64_t>(pu * d.vp + pv) * K + static_cast<int64_t>(u) * d.vq + v]) * gscale;
-      const float a = rnd(ld_f(d.f0, d.f_dtype, pu * d.uq + u), fround);
-      acc = fmaf(a, g, acc);
-      float s = g * b;
+  const int64_t e0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * VEC;
+  const bool live = e0 < plane;
+  const int pv = live ? static_cast<int>(e0 / d.vq) : 0;
+  const int v = live ? static_cast<int>(e0 % d.vq) : 0;  // VEC divides vq: the vector stays in one row
+  float b[VEC], acc[VEC];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) atomicAdd(SMEM_W1 ? &s_w1[pu * d.uq + u] : &g_w1[pu * d.uq + u], s);
+  for (int i = 0; i < VEC; ++i) {
+    b[i] = live ? rnd(ld_f(d.f1, d.f_dtype, e0 + i), fround) : 0.f;
+    acc[i] = 0.f;
+  }
+  const int lane = threadIdx.x & 31;
+  const float* row = dW + static_cast<int64_t>(pu * d.vp + pv) * K + v;
+  for (int u = 0; u < d.uq; ++u) {
+    float g[VEC];
+    if (live) {
+      if (VEC == 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(row + static_cast<int64_t>(u) * d.vq));
+        g[0] = t.x; g[1 % VEC] = t.y; g[2 % VEC] = t.z; g[3 % VEC] = t.w;
+      } else {
+        g[0] = __ldg(row + static_cast<int64_t>(u) * d.vq);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) g[i] = 0.f;
     }
+    const float a = rnd(ld_f(d.f0, d.f_dtype, pu * d.uq + u), fround);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      g[i] *= gscale;
+      acc[i] = fmaf(a, g[i], acc[i]);
+      s = fmaf(g[i], b[i], s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) atomicAdd(&s_w1[u], s);
   }
-  if (live) g_w2[e] = acc;
-  if (SMEM_W1) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < n_w1; i += blockDim.x) atomicAdd(&g_w1[i], s_w1[i]);
+  if (live) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) atomicAdd(&g_w2[e0 + i], acc[i]);
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < d.uq; i += blockDim.x) atomicAdd(&g_w1[pu * d.uq + i], s_w1[i]);
 }
 
 // (IA)^3: g_w[c] = mult * sum dW[n,k] * W[n,k] over the row (or the input-channel columns)

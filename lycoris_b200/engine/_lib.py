@@ -24,6 +24,8 @@ EXPORTED_SYMBOLS = (
     "lyco_device_check",
     "lyco_launch_count",
     "lyco_gemm",
+    "lyco_conv2d_fprop",
+    "lyco_conv2d_wgrad",
     "lyco_merge_weight",
     "lyco_factor_grads",
 )
@@ -82,6 +84,18 @@ def _bind(lib):
         c_void_p, c_int,  # bias
         c_int, c_int, c_int,  # M N K
         c_int, c_int, c_void_p,  # ab_dtype, split_k, stream
+    ]
+    lib.lyco_conv2d_fprop.restype = c_int
+    lib.lyco_conv2d_fprop.argtypes = [
+        c_void_p, c_void_p, c_void_p, c_void_p, c_int,  # X Wk Y bias bias_dtype
+        c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,  # Nb H W C O R S pad_h pad_w stride
+        c_int, c_void_p,  # dtype stream
+    ]
+    lib.lyco_conv2d_wgrad.restype = c_int
+    lib.lyco_conv2d_wgrad.argtypes = [
+        c_void_p, c_void_p, c_void_p,  # X dY dW
+        c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,  # Nb H W C O R S pad_h pad_w stride
+        c_int, c_int, c_void_p,  # dtype split_k stream
     ]
     lib.lyco_merge_weight.restype = c_int
     lib.lyco_merge_weight.argtypes = [POINTER(DeltaDesc), c_void_p, c_void_p, c_void_p]

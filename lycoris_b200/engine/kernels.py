@@ -99,6 +99,47 @@ def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, out_dtype=None, split_k=0, 
     return out
 
 
+def conv2d_supported(x, weight_shape, stride, padding, dilation, groups) -> bool:
+    """The implicit-GEMM kernels take NHWC (channels_last) activations, C % 64 == 0, O % 8 == 0."""
+    if x.dim() != 4 or len(weight_shape) != 4 or x.dtype not in (torch.bfloat16, torch.float16):
+        return False
+    O, C, R, S = weight_shape
+    if groups != 1 or tuple(dilation) != (1, 1) or stride[0] != stride[1] or not (1 <= stride[0] <= 8):
+        return False
+    if C % 64 or O % 8 or x.data_ptr() % 16:
+        return False
+    return x.is_contiguous(memory_format=torch.channels_last)
+
+
+def conv2d_fprop(x, wk, bias, R, S, pad, stride):
+    """``x``: [Nb, C, H, W] in channels_last storage; ``wk``: [O, R*S*C] (filter as [O,R,S,C]).
+    Returns y [Nb, O, P, Q] in channels_last storage."""
+    _require_cuda(x, wk, bias)
+    Nb, C, H, W = x.shape
+    O = wk.shape[0]
+    P = (H + 2 * pad[0] - R) // stride + 1
+    Q = (W + 2 * pad[1] - S) // stride + 1
+    y = torch.empty((Nb, O, P, Q), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+    rc = _lib.load().lyco_conv2d_fprop(
+        _ptr(x), _ptr(wk), _ptr(y), _ptr(bias), dtype_code(bias.dtype) if bias is not None else 0,
+        Nb, H, W, C, O, R, S, pad[0], pad[1], stride, dtype_code(x.dtype), _stream())
+    _lib.check(rc, "conv2d_fprop")
+    return y
+
+
+def conv2d_wgrad(x, dy, R, S, pad, stride, split_k=0):
+    """fp32 [O, R*S*C] weight gradient from channels_last ``x`` [Nb,C,H,W] and ``dy`` [Nb,O,P,Q]."""
+    _require_cuda(x, dy)
+    Nb, C, H, W = x.shape
+    O = dy.shape[1]
+    dw = torch.empty((O, R * S * C), device=x.device, dtype=torch.float32)
+    rc = _lib.load().lyco_conv2d_wgrad(
+        _ptr(x), _ptr(dy), _ptr(dw), Nb, H, W, C, O, R, S, pad[0], pad[1], stride, dtype_code(x.dtype),
+        int(split_k), _stream())
+    _lib.check(rc, "conv2d_wgrad")
+    return dw
+
+
 def make_desc(algo, out_dim, in_dim, *, factors, w_dtype, rank=0, up=0, uq=0, vp=0, vq=0, on_input=0,
               ia3_group=1, pre_round=0, pre_dtype=None, m_in=1.0, m_pre=1.0, m_post1=1.0, m_post2=1.0):
     f = list(factors) + [None] * (4 - len(factors))
@@ -150,6 +191,6 @@ def factor_grads(desc: DeltaDesc, dW: torch.Tensor, W, shapes):
 
 
 __all__ = [
-    "gemm", "gemm_supported", "make_desc", "merge_weight", "factor_grads", "dtype_code",
+    "gemm", "gemm_supported", "conv2d_supported", "conv2d_fprop", "conv2d_wgrad", "make_desc", "merge_weight", "factor_grads", "dtype_code",
     "ALGO_LOCON", "ALGO_LOHA", "ALGO_LOKR", "ALGO_IA3", "ALGO_DYLORA", "BF16", "F16", "F32",
 ]

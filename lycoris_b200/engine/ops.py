@@ -13,6 +13,7 @@ itself, and ~6 launches per layer-step instead of 35–60 ATen ops.
 
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 
 import torch
@@ -96,12 +97,45 @@ def _dense_tn_f32(a, b):
     return (a.t() @ b).float()
 
 
+# LYCO_CONV_IMPL=cudnn routes every k>1 convolution through aten/cuDNN (on the merged weight) instead of
+# the implicit-GEMM kernels; the default uses the engine whenever the layer is eligible (NHWC, C % 64 == 0).
+_CONV_ENGINE = os.environ.get("LYCO_CONV_IMPL", "engine") != "cudnn"
+
+
+def _conv_engine_ok(x, w, cp):
+    return (_CONV_ENGINE and w.dim() == 4 and not isinstance(cp["padding"], str)
+            and K.conv2d_supported(x, w.shape, cp["stride"], cp["padding"], cp["dilation"], cp["groups"]))
+
+
 def _conv_forward(x, w, bias, cp):
+    if _conv_engine_ok(x, w, cp):
+        O, C, R, S = w.shape
+        wk = w.permute(0, 2, 3, 1).reshape(O, R * S * C)  # filter taps outermost, channels contiguous
+        return K.conv2d_fprop(x, wk, bias, R, S, cp["padding"], cp["stride"][0])
     return torch.ops.aten.convolution(x, w, bias, cp["stride"], cp["padding"], cp["dilation"], False,
                                       [0] * len(cp["stride"]), cp["groups"])
 
 
 def _conv_backward(dy, x, w, cp, need_x, need_w):
+    """(dx, dw) with dw shaped like ``w`` (fp32 from the engine, w.dtype from the library path)."""
+    if _conv_engine_ok(x, w, cp):
+        O, C, R, S = w.shape
+        st, pad = cp["stride"][0], cp["padding"]
+        dyc = dy.contiguous(memory_format=torch.channels_last)
+        dx = dw = None
+        if need_x:
+            if st == 1 and O % 64 == 0 and C % 8 == 0 and pad[0] <= R - 1 and pad[1] <= S - 1:
+                # input gradient = the same implicit GEMM over dY with the flipped, transposed filter
+                wd = w.flip(2, 3).permute(1, 2, 3, 0).reshape(C, R * S * O)
+                dx = K.conv2d_fprop(dyc, wd, None, R, S, (R - 1 - pad[0], S - 1 - pad[1]), 1)
+            else:
+                dx = torch.ops.aten.convolution_backward(
+                    dyc, x, w, None, cp["stride"], cp["padding"], cp["dilation"], False, [0, 0], cp["groups"],
+                    [True, False, False])[0]
+        if need_w:
+            dwk = K.conv2d_wgrad(x, dyc, R, S, pad, st)  # [O, R*S*C] fp32
+            dw = dwk.view(O, R, S, C).permute(0, 3, 1, 2).contiguous()
+        return dx, dw
     dx, dw, _ = torch.ops.aten.convolution_backward(
         dy, x, w, None, cp["stride"], cp["padding"], cp["dilation"], False, [0] * len(cp["stride"]),
         cp["groups"], [need_x, need_w, False])
@@ -211,6 +245,8 @@ class _MergedContraction(torch.autograd.Function):
                 dw = _dense_tn_f32(dy2, x2).to(Wm.dtype)
         else:
             dx, dw = _conv_backward(dy.contiguous(), x, Wm, conv, need_x, need_w)
+            if dw is not None and dw.dtype != Wm.dtype:
+                dw = dw.to(Wm.dtype)
         return dx, dw, None, None
 
 

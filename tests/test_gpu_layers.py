@@ -180,3 +180,61 @@ def test_zero_init_adapter_is_identity_and_engine_was_used():
     assert _lib.launch_count() >= before + 2, "the CUDA extension did not run"
     # dW == 0 -> W' == W exactly; single fp32-accumulated contraction vs cuBLAS: <= 1 bf16 ulp apart
     assert float((y1.float() - y0.float()).abs().max()) <= 2.0 ** -7 * float(y0.float().abs().max())
+
+
+CONV_ENGINE_CASES = [
+    # (algo ctor, Nb, C, O, H, W, k, stride)
+    ("lokr", 2, 64, 128, 12, 10, 3, 1),
+    ("lokr", 2, 128, 64, 9, 9, 3, 1),
+    ("locon", 3, 64, 64, 8, 8, 3, 1),
+    ("loha", 2, 64, 72, 8, 8, 3, 1),     # O not a multiple of 64: dgrad takes the library path
+    ("lokr", 2, 64, 64, 16, 16, 3, 2),   # stride 2: fprop + wgrad on the engine, dgrad library
+]
+
+
+@pytest.mark.parametrize("algo,Nb,C,O,H,W,k,stride", CONV_ENGINE_CASES)
+def test_conv_implicit_gemm_layer_matches_oracle(algo, Nb, C, O, H, W, k, stride):
+    """3x3 convolutions on channels_last activations run the TMA-im2col implicit GEMM (fprop, dgrad as
+    fprop on dY with the flipped filter, wgrad) — compared with the oracle (cuDNN eager) on device."""
+    import torch.nn as nn
+
+    import lycoris_b200 as L
+    from lycoris_b200.engine import _lib
+    from oracle import lyco_oracle as O_
+
+    torch.manual_seed(C + O + H)
+    base = nn.Conv2d(C, O, k, stride, k // 2).cuda().to(torch.bfloat16)
+    for p in base.parameters():
+        p.requires_grad_(False)
+    if algo == "lokr":
+        mod = L.LokrModule("c", base, 1.0, 100000, 1, factor=8).cuda()
+        with torch.no_grad():
+            mod.lokr_w2.normal_(0, 0.02)
+        oalgo, cfg = "lokr", {"scale": mod.scale, "multiplier": 1.0}
+    elif algo == "locon":
+        mod = L.LoConModule("c", base, 1.0, 8, 4).cuda()
+        with torch.no_grad():
+            mod.lora_up.weight.normal_(0, 0.05)
+        oalgo, cfg = "locon", {"scale": mod.scale, "multiplier": 1.0}
+    else:
+        mod = L.LohaModule("c", base, 1.0, 4, 2).cuda()
+        with torch.no_grad():
+            mod.hada_w2_a.normal_(0, 0.1)
+        oalgo, cfg = "loha", {"scale": mod.scale, "multiplier": 1.0}
+    x = torch.randn(Nb, C, H, W, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    x.requires_grad_(True)
+    before = _lib.launch_count()
+    mod.apply_to()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = base(x)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    mod.restore()
+    assert _lib.launch_count() - before >= 5  # merge + fprop + (dgrad) + wgrad + factor grads
+    p = {kk: v.detach() for kk, v in mod.named_parameters()}
+    conv = dict(stride=base.stride, padding=base.padding, dilation=base.dilation, groups=1)
+    oy, odx, og = O_.layer_forward_backward(oalgo, x.detach(), base.weight, base.bias, p, cfg, dy, conv, torch.bfloat16)
+    assert float((y.detach().float() - oy.float()).abs().max()) <= Y_REL * float(oy.float().abs().max())
+    assert float((x.grad.float() - odx.float()).abs().max()) <= Y_REL * float(odx.float().abs().max())
+    for kk, g in og.items():
+        assert rel_err(getattr(mod, kk.split(".")[0]).weight.grad if "." in kk else getattr(mod, kk).grad, g) <= G_REL, kk

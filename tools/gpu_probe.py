@@ -138,6 +138,56 @@ def case_weight(algo, N, K, r, fdt="f32"):
     return res
 
 
+def case_conv(Nb, H, W, C, O, R, pad, stride):
+    import torch
+    import torch.nn.functional as F
+    from lycoris_b200.engine import kernels as k
+
+    torch.manual_seed(3)
+    dt = torch.bfloat16
+    x = torch.randn(Nb, C, H, W, device="cuda", dtype=dt).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(O, C, R, R, device="cuda") / (C * R * R) ** 0.5).to(dt)
+    b = torch.randn(O, device="cuda", dtype=dt)
+    res = {}
+    wk = w.permute(0, 2, 3, 1).reshape(O, R * R * C)
+    y = k.conv2d_fprop(x, wk, b, R, R, (pad, pad), stride)
+    torch.cuda.synchronize()
+    xr = x.float().requires_grad_(True)
+    wr = w.float().requires_grad_(True)
+    ref = F.conv2d(xr, wr, b.float(), stride=stride, padding=pad)
+    res["fprop_rel"] = ((y.float() - ref).abs().max() / ref.abs().max()).item()
+    dy = torch.randn_like(ref).to(dt).contiguous(memory_format=torch.channels_last)
+    ref.backward(dy.float())
+    dwk = k.conv2d_wgrad(x, dy, R, R, (pad, pad), stride)
+    dw = dwk.view(O, R, R, C).permute(0, 3, 1, 2)
+    res["wgrad_rel"] = ((dw - wr.grad).abs().max() / wr.grad.abs().max()).item()
+    ok = res["fprop_rel"] < 1e-2 and res["wgrad_rel"] < 1e-3
+    if stride == 1 and O % 64 == 0:
+        wd = w.flip(2, 3).permute(1, 2, 3, 0).reshape(C, R * R * O)
+        dx = k.conv2d_fprop(dy, wd, None, R, R, (R - 1 - pad, R - 1 - pad), 1)
+        res["dgrad_rel"] = ((dx.float() - xr.grad).abs().max() / xr.grad.abs().max()).item()
+        ok = ok and res["dgrad_rel"] < 1e-2
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    flops = 2.0 * y.numel() * C * R * R
+    for name, fn in (("fprop", lambda: k.conv2d_fprop(x, wk, b, R, R, (pad, pad), stride)),
+                     ("wgrad", lambda: k.conv2d_wgrad(x, dy, R, R, (pad, pad), stride)),
+                     ("cudnn_fprop", lambda: F.conv2d(x, w, b, stride=stride, padding=pad)),
+                     ("cudnn_bwd", lambda: torch.ops.aten.convolution_backward(dy, x, w, None, [stride] * 2, [pad] * 2, [1, 1], False, [0, 0], 1, [True, True, False]))):
+        for _ in range(3):
+            fn()
+        e0.record()
+        for _ in range(5):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        res[name + "_ms"] = ms
+        res[name + "_tflops"] = flops * (2 if name == "cudnn_bwd" else 1) / ms / 1e9
+    res["ok"] = bool(ok)
+    return res
+
+
 CASES = []
 for bn_shape in [(256, 256, 128), (128, 64, 64), (1000, 328, 200)]:
     CASES.append(("gemm", dict(M=bn_shape[0], N=bn_shape[1], K=bn_shape[2], a_mn=False, b_mn=False, out="16", bias=False)))
@@ -172,6 +222,15 @@ CASES += [
     ("gemm", dict(M=8192, N=1280, K=1280, a_mn=False, b_mn=False, out="16", bias=True)),
     ("weight", dict(algo="locon", N=1280, K=1280, r=16)),
     ("weight", dict(algo="locon", N=320, K=2880, r=8, fdt="bf16")),
+    ("conv", dict(Nb=2, H=8, W=8, C=64, O=64, R=3, pad=1, stride=1)),
+    ("conv", dict(Nb=2, H=12, W=10, C=128, O=192, R=3, pad=1, stride=1)),
+    ("conv", dict(Nb=3, H=9, W=7, C=64, O=72, R=3, pad=1, stride=1)),
+    ("conv", dict(Nb=2, H=16, W=16, C=64, O=64, R=3, pad=1, stride=2)),
+    ("conv", dict(Nb=2, H=16, W=16, C=320, O=320, R=3, pad=1, stride=1)),
+    ("conv", dict(Nb=8, H=32, W=32, C=1280, O=1280, R=3, pad=1, stride=1)),
+    ("conv", dict(Nb=8, H=128, W=128, C=320, O=320, R=3, pad=1, stride=1)),
+    ("conv", dict(Nb=8, H=64, W=64, C=640, O=640, R=3, pad=1, stride=1)),
+    ("conv", dict(Nb=8, H=32, W=32, C=2560, O=1280, R=3, pad=1, stride=1)),
     ("weight", dict(algo="loha", N=1280, K=1280, r=32)),
     ("weight", dict(algo="lokr", N=1280, K=1280, r=0)),
     ("weight", dict(algo="lokr", N=10240, K=1280, r=0, fdt="bf16")),
@@ -182,7 +241,7 @@ CASES += [
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "--one":
         kind, kw = CASES[int(sys.argv[2])]
-        fn = case_gemm if kind == "gemm" else case_weight
+        fn = {"gemm": case_gemm, "weight": case_weight, "conv": case_conv}[kind]
         print("RESULT " + json.dumps(fn(**kw)))
         return
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
