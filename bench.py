@@ -537,6 +537,8 @@ def run_reference_gpu(args):
 
         torch.manual_seed(1)
         net = kohya.create_network(1.0, na["network_dim"], na["network_alpha"], None, None, unet, **na["kw"])
+        for lora in net.loras:
+            net.add_module(lora.lora_name, lora)
         net.to(device)
         for lora in net.loras:  # patch the oracle's forward instead of the engine's
             org = lora.org_module[0]
@@ -549,7 +551,6 @@ def run_reference_gpu(args):
                 return O.layer_forward("lokr", x, _o.weight, _o.bias, p, {"scale": _l.scale, "multiplier": 1.0}, _c)
 
             org.forward = fwd
-            net.add_module(lora.lora_name, lora)
     perturb_zero_factors(net, 1)
     net.requires_grad_(True)
     batch = unet.synthetic_batch(args.batch, "cpu", torch.bfloat16, seed=2, sample_size=args.sample_size or None)

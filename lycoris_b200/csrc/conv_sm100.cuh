@@ -38,13 +38,10 @@ __device__ __forceinline__ void tma_im2col_4d(void* smem_dst, const CUtensorMap*
       : "memory");
 }
 
-template <int BLOCK_N, int MODE, int EPI>
+template <int MODE, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 conv_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                  const ConvParams cp) {
-  using Cfg = GemmCfg<BLOCK_N>;
-  constexpr int STAGES = Cfg::STAGES;
-  constexpr int STAGE_BYTES = Cfg::STAGE_BYTES;
+                  const __grid_constant__ CUtensorMap tmap_c, const ConvParams cp) {
   constexpr bool A_MN = (MODE == MODE_WGRAD);
   constexpr bool B_MN = (MODE == MODE_WGRAD);
   const GemmParams& p = cp.g;
@@ -52,34 +49,25 @@ conv_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint8_t* epi_smem = smem + GEMM_RING_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + GEMM_EPI_BYTES);
+  uint64_t* empty_bar = full_bar + GEMM_MAX_STAGES;
+  uint64_t* tfull_bar = empty_bar + GEMM_MAX_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int block_n = p.block_n;
+  const int stage_bytes = GEMM_A_BYTES + block_n * GEMM_BLOCK_K * 2;
+  const int stages = p.stages;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_a);
     ptx::prefetch_tmap(&tmap_b);
+    if (EPI == EPI_STORE16) ptx::prefetch_tmap(&tmap_c);
   }
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&empty_bar[s], 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      ptx::mbar_init(&tfull_bar[a], 1);
-      ptx::mbar_init(&tempty_bar[a], 4);
-    }
-    ptx::fence_mbar_init();
-  }
-  if (warp == 2) ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
+  gemm_setup<false>(full_bar, empty_bar, tfull_bar, tempty_bar, tmem_slot, stages, warp, lane);
   const uint32_t tmem_base = *tmem_slot;
 
   const int total = p.m_tiles * p.n_tiles * p.splits;
@@ -105,17 +93,17 @@ conv_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           const int tap = kb / cp.CB, cb = kb - tap * cp.CB;
           const int fr = tap / cp.S, fs = tap - fr * cp.S;
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          ptx::mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-          uint8_t* sa = smem + stage * STAGE_BYTES;
+          ptx::mbar_expect_tx(&full_bar[stage], stage_bytes);
+          uint8_t* sa = smem + stage * stage_bytes;
           uint8_t* sb = sa + GEMM_A_BYTES;
           tma_im2col_4d(sa, &tmap_a, &full_bar[stage], cb * 64, w0, h0, img, static_cast<uint16_t>(fs),
                         static_cast<uint16_t>(fr));
-          ptx::tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * GEMM_BLOCK_K, n_idx * BLOCK_N);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          ptx::tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * GEMM_BLOCK_K, n_idx * block_n);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       } else {
         const int tap = n_idx / cp.tiles_per_tap;
-        const int c0 = (n_idx - tap * cp.tiles_per_tap) * BLOCK_N;
+        const int c0 = (n_idx - tap * cp.tiles_per_tap) * block_n;
         const int fr = tap / cp.S, fs = tap - fr * cp.S;
         for (int kb = kb0; kb < kb1; ++kb) {
           const int m0 = kb * GEMM_BLOCK_K;  // first pixel of this reduction block
@@ -123,24 +111,23 @@ conv_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           const int py = rem / cp.Q, px = rem - py * cp.Q;
           const int w0 = px * cp.stride + cp.low_w, h0 = py * cp.stride + cp.low_h;
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          ptx::mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-          uint8_t* sa = smem + stage * STAGE_BYTES;
+          ptx::mbar_expect_tx(&full_bar[stage], stage_bytes);
+          uint8_t* sa = smem + stage * stage_bytes;
           uint8_t* sb = sa + GEMM_A_BYTES;
 #pragma unroll
           for (int j = 0; j < GEMM_BLOCK_M / 64; ++j)
             ptx::tma_load_2d(sa + j * GEMM_ATOM_BYTES, &tmap_a, &full_bar[stage], m_idx * GEMM_BLOCK_M + j * 64,
                              kb * GEMM_BLOCK_K);
-#pragma unroll
-          for (int j = 0; j < BLOCK_N / 64; ++j)
+          for (int j = 0; j < block_n / 64; ++j)
             tma_im2col_4d(sb + j * GEMM_ATOM_BYTES, &tmap_b, &full_bar[stage], c0 + j * 64, w0, h0, img,
                           static_cast<uint16_t>(fs), static_cast<uint16_t>(fr));
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1 && lane == 0) {
     // -------------------------------------------------------------- MMA issuer
-    const uint32_t idesc = ptx::make_idesc_f16(p.fmt, GEMM_BLOCK_M, BLOCK_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    const uint32_t idesc = ptx::make_idesc_f16(p.fmt, GEMM_BLOCK_M, block_n, A_MN ? 1 : 0, B_MN ? 1 : 0);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -151,22 +138,13 @@ conv_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const int kb1 = static_cast<int>(static_cast<int64_t>(split + 1) * p.k_blocks / p.splits);
       ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       ptx::tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      const uint32_t d_tmem = tmem_base + acc * 256;
       for (int kb = kb0; kb < kb1; ++kb) {
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after();
-        const uint32_t sa = ptx::smem_u32(smem + stage * STAGE_BYTES);
-        const uint32_t sb = sa + GEMM_A_BYTES;
-#pragma unroll
-        for (int kk = 0; kk < GEMM_BLOCK_K / GEMM_UMMA_K; ++kk) {
-          const uint64_t da = A_MN ? ptx::make_smem_desc(sa + kk * 2048, GEMM_ATOM_BYTES, 1024)
-                                   : ptx::make_smem_desc(sa + kk * 32, 16, 1024);
-          const uint64_t db = B_MN ? ptx::make_smem_desc(sb + kk * 2048, GEMM_ATOM_BYTES, 1024)
-                                   : ptx::make_smem_desc(sb + kk * 32, 16, 1024);
-          ptx::umma_f16(d_tmem, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
-        }
-        ptx::umma_commit(&empty_bar[stage]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        const uint32_t sa = ptx::smem_u32(smem + stage * stage_bytes);
+        gemm_issue_kblock<false, A_MN, B_MN>(sa, sa + GEMM_A_BYTES, d_tmem, idesc, kb == kb0, &empty_bar[stage]);
+        if (++stage == stages) { stage = 0; phase ^= 1; }
       }
       ptx::umma_commit(&tfull_bar[acc]);
       acc ^= 1;
@@ -175,6 +153,8 @@ conv_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue
     const int ew = warp - 4;
+    uint8_t* stage_buf = epi_smem + ew * 4096;
+    int buf = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
@@ -183,40 +163,26 @@ conv_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const int m_idx = tile / p.n_tiles;
       int col_base, col_limit;
       if (MODE == MODE_FPROP) {
-        col_base = n_idx * BLOCK_N;
+        col_base = n_idx * block_n;
         col_limit = p.N;
       } else {
         const int tap = n_idx / cp.tiles_per_tap;
-        col_base = tap * cp.C + (n_idx - tap * cp.tiles_per_tap) * BLOCK_N;
+        col_base = tap * cp.C + (n_idx - tap * cp.tiles_per_tap) * block_n;
         col_limit = (tap + 1) * cp.C;  // columns past this tap's channels are padding of the tile
       }
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tc_fence_after();
-      const int row = m_idx * GEMM_BLOCK_M + ew * 32 + lane;
-      const uint32_t t_row = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(ew * 32) << 16);
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(t_row + c * 32, r);
-        ptx::tmem_ld_wait();
-        if (c == BLOCK_N / 32 - 1) {
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
-        }
-        store_chunk<EPI>(r, row, col_base + c * 32, p, col_limit);
-      }
+      const int row0 = m_idx * GEMM_BLOCK_M + ew * 32;
+      const uint32_t t_row = tmem_base + acc * 256 + (static_cast<uint32_t>(ew * 32) << 16);
+      gemm_epilogue_tile<false, EPI>(t_row, row0, col_base, col_limit, block_n, p, &tmap_c, stage_buf, buf,
+                                     &tempty_bar[acc], lane);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (EPI == EPI_STORE16 && lane == 0) ptx::tma_store_wait_read<0>();
   }
 
-  ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
-  }
+  gemm_teardown<false>(tmem_base, warp);
 }
 
 }  // namespace lyco

@@ -2,17 +2,25 @@
 //
 //   C[M,N] (+)= A[M,K] * B[N,K]^T (+ bias)      16-bit operands, fp32 accumulation in TMEM
 //
-// One CTA per SM, 256 threads:
+// 256 threads per CTA, one CTA per SM:
 //   warp 0      TMA producer  (one elected lane)      global -> smem ring (SWIZZLE_128B boxes)
-//   warp 1      MMA issuer    (one elected lane)      tcgen05.mma 128 x BLOCK_N x 16, D in TMEM
+//   warp 1      MMA issuer    (one elected lane)      tcgen05.mma, D in TMEM
 //   warp 2      TMEM allocator / deallocator
-//   warps 4..7  epilogue: tcgen05.ld -> registers -> (bias, cast) -> global
-// Three pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue, two
-// accumulator stages so the epilogue of tile i overlaps the main loop of tile i+1), and the
-// static persistent tile schedule.
+//   warps 4..7  epilogue: tcgen05.ld -> registers -> (bias, cast) -> swizzled smem -> TMA store
+//               (fp32 outputs: direct 16-byte stores / red.global.add.v4.f32 for split-K partials)
+// Three pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue, two accumulator
+// stages so the epilogue of tile i overlaps the main loop of tile i+1), and the static persistent
+// tile schedule.  BLOCK_N is a RUNTIME multiple of 32 (32..256) picked per problem by the host so
+// that the last wave of tiles is as full as possible.
+//
+// PAIR = true: two CTAs of one TPC (cluster 2x1x1) share a 256 x BLOCK_N tile with
+// tcgen05.mma.cta_group::2 — each stages its own 128 rows of A and HALF of the B tile, which cuts the
+// L2 -> SM feed per CTA from (128 + BLOCK_N) to (128 + BLOCK_N/2) rows per k-block (the single-CTA
+// kernel is feed-bound at 128x256).  The leader CTA issues the MMAs; TMA completion of both CTAs is
+// signalled on the leader's full barrier; tcgen05.commit multicasts to both CTAs.
 //
 // Either operand may be K-major (reduction index contiguous in memory) or MN-major (output index
-// contiguous): the three contractions of a wrapped layer are then all served without transposes
+// contiguous): the three contractions of a wrapped layer are all served without transposes
 //   forward  Y  = X  * W'^T        A = X  [M,K]  K-major    B = W' [N,K]  K-major
 //   dgrad    dX = dY * W'          A = dY [M,N]  K-major    B = W' [N,K]  MN-major (as [K_out, N_red])
 //   wgrad    dW'= dY^T * X         A = dY [M,N]  MN-major   B = X  [M,K]  MN-major, split over M
@@ -24,13 +32,17 @@
 
 namespace lyco {
 
-constexpr int GEMM_BLOCK_M = 128;
-constexpr int GEMM_BLOCK_K = 64;  // 64 x 16-bit = 128 B = one swizzle row
+constexpr int GEMM_BLOCK_M = 128;   // rows per CTA (a pair covers 256)
+constexpr int GEMM_BLOCK_K = 64;    // 64 x 16-bit = 128 B = one swizzle row
 constexpr int GEMM_UMMA_K = 16;
 constexpr int GEMM_THREADS = 256;
 constexpr int GEMM_A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;  // 16 KiB
 constexpr int GEMM_ATOM_BYTES = 64 * GEMM_BLOCK_K * 2;         // one MN-major 64x64 box, 8 KiB
 constexpr int GEMM_RING_BYTES = 192 * 1024;
+constexpr int GEMM_MAX_STAGES = 8;
+constexpr int GEMM_EPI_BYTES = 4 * 2 * 2048;   // 4 epilogue warps x 2 staging buffers x (32 rows x 64 B)
+constexpr int GEMM_TMEM_COLS = 512;            // two accumulator stages at columns 0 and 256
+constexpr int GEMM_SMEM_BYTES = GEMM_RING_BYTES + GEMM_EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
 enum { EPI_STORE16 = 0, EPI_STORE_F32 = 1, EPI_ATOMIC_F32 = 2 };
 
@@ -40,17 +52,10 @@ struct GemmParams {
   int64_t ldc;
   int M, N, K;
   int m_tiles, n_tiles, splits, k_blocks;
-  int fmt;         // operand / 16-bit output format: 0 = f16, 1 = bf16
-  int bias_dtype;  // LYCO_BF16 / LYCO_F16 / LYCO_F32
-};
-
-template <int BLOCK_N>
-struct GemmCfg {
-  static constexpr int B_BYTES = BLOCK_N * GEMM_BLOCK_K * 2;
-  static constexpr int STAGE_BYTES = GEMM_A_BYTES + B_BYTES;
-  static constexpr int STAGES = (GEMM_RING_BYTES / STAGE_BYTES) > 8 ? 8 : (GEMM_RING_BYTES / STAGE_BYTES);
-  static constexpr int TMEM_COLS = 2 * BLOCK_N;  // two accumulator stages
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  int block_n;      // columns per tile (multiple of 32; MN-major B: of 64, pairs: of 128)
+  int stages;       // smem ring depth for this block_n
+  int fmt;          // operand / 16-bit output format: 0 = f16, 1 = bf16
+  int bias_dtype;   // LYCO_BF16 / LYCO_F16 / LYCO_F32
 };
 
 __device__ __forceinline__ float load_scalar(const void* p, int dtype, int64_t i) {
@@ -68,243 +73,324 @@ __device__ __forceinline__ uint32_t pack16(float a, float b, int fmt) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-// Epilogue for one 32-column chunk of one accumulator row held in registers (fp32 bit patterns).
-template <int EPI>
-__device__ __forceinline__ void store_chunk(const uint32_t (&r)[32], int row, int col0, const GemmParams& p,
-                                            int col_limit = -1) {
-  const int N = col_limit < 0 ? p.N : col_limit;  // first column this tile must not write
-  if (row >= p.M || col0 >= N) return;
-  const bool full = (col0 + 32 <= N);
-  if (EPI == EPI_STORE16) {
-    float v[32];
+// v[0..31] += bias[col0 .. col0+31]  (columns >= n_limit untouched)
+__device__ __forceinline__ void add_bias32(float (&v)[32], const GemmParams& p, int col0, int n_limit) {
+  if (p.bias == nullptr) return;
+  const bool full = col0 + 32 <= n_limit;
+  if (full && p.bias_dtype != 2 && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {
+    // 32 x 16-bit values = four 16-byte loads (every lane reads the same addresses: L1 broadcast)
+    const uint4* bp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.bias) + col0);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-    if (p.bias != nullptr) {
-      if (full && p.bias_dtype != 2 && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {
-        // 32 x 16-bit bias values = four 16-byte loads (every lane reads the same addresses: L1 broadcast)
-        const uint4* bp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.bias) + col0);
+    for (int q = 0; q < 4; ++q) {
+      const uint4 bv = __ldg(bp + q);
+      const uint32_t w[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint4 bv = __ldg(bp + q);
-          const uint32_t w[4] = {bv.x, bv.y, bv.z, bv.w};
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            float lo, hi;
-            if (p.bias_dtype == 0) {
-              lo = __uint_as_float(w[t] << 16);
-              hi = __uint_as_float(w[t] & 0xFFFF0000u);
-            } else {
-              const __half2 h = *reinterpret_cast<const __half2*>(&w[t]);
-              lo = __low2float(h);
-              hi = __high2float(h);
-            }
-            v[8 * q + 2 * t] += lo;
-            v[8 * q + 2 * t + 1] += hi;
-          }
+      for (int t = 0; t < 4; ++t) {
+        float lo, hi;
+        if (p.bias_dtype == 0) {
+          lo = __uint_as_float(w[t] << 16);
+          hi = __uint_as_float(w[t] & 0xFFFF0000u);
+        } else {
+          const __half2 h = *reinterpret_cast<const __half2*>(&w[t]);
+          lo = __low2float(h);
+          hi = __high2float(h);
         }
-      } else if (full) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += load_scalar(p.bias, p.bias_dtype, col0 + j);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (col0 + j < N) v[j] += load_scalar(p.bias, p.bias_dtype, col0 + j);
+        v[8 * q + 2 * t] += lo;
+        v[8 * q + 2 * t + 1] += hi;
       }
-    }
-    uint16_t* crow = reinterpret_cast<uint16_t*>(p.C) + static_cast<int64_t>(row) * p.ldc + col0;
-    if (full) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        uint4 o;
-        o.x = pack16(v[8 * q + 0], v[8 * q + 1], p.fmt);
-        o.y = pack16(v[8 * q + 2], v[8 * q + 3], p.fmt);
-        o.z = pack16(v[8 * q + 4], v[8 * q + 5], p.fmt);
-        o.w = pack16(v[8 * q + 6], v[8 * q + 7], p.fmt);
-        reinterpret_cast<uint4*>(crow)[q] = o;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (col0 + j < N) crow[j] = static_cast<uint16_t>(pack16(v[j], 0.f, p.fmt) & 0xFFFF);
     }
   } else {
-    float* crow = reinterpret_cast<float*>(p.C) + static_cast<int64_t>(row) * p.ldc + col0;
-    if (full) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        if (EPI == EPI_STORE_F32) {
-          reinterpret_cast<float4*>(crow)[q] =
-              make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
-                          __uint_as_float(r[4 * q + 3]));
-        } else {
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow + 4 * q),
-                       "f"(__uint_as_float(r[4 * q])), "f"(__uint_as_float(r[4 * q + 1])),
-                       "f"(__uint_as_float(r[4 * q + 2])), "f"(__uint_as_float(r[4 * q + 3]))
-                       : "memory");
-        }
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (col0 + j < N) {
-          if (EPI == EPI_STORE_F32) crow[j] = __uint_as_float(r[j]);
-          else atomicAdd(crow + j, __uint_as_float(r[j]));
-        }
-    }
+    for (int j = 0; j < 32; ++j)
+      if (col0 + j < n_limit) v[j] += load_scalar(p.bias, p.bias_dtype, col0 + j);
   }
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                  const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
-  using Cfg = GemmCfg<BLOCK_N>;
-  constexpr int STAGES = Cfg::STAGES;
-  constexpr int STAGE_BYTES = Cfg::STAGE_BYTES;
+// fp32 epilogue for one 32-column chunk of one accumulator row (plain store or split-K reduction)
+template <int EPI>
+__device__ __forceinline__ void store_chunk_f32(const uint32_t (&r)[32], int row, int col0, const GemmParams& p,
+                                                int n_limit) {
+  if (row >= p.M || col0 >= n_limit) return;
+  float* crow = reinterpret_cast<float*>(p.C) + static_cast<int64_t>(row) * p.ldc + col0;
+  if (col0 + 32 <= n_limit) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      if (EPI == EPI_STORE_F32) {
+        reinterpret_cast<float4*>(crow)[q] =
+            make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                        __uint_as_float(r[4 * q + 3]));
+      } else {
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow + 4 * q),
+                     "f"(__uint_as_float(r[4 * q])), "f"(__uint_as_float(r[4 * q + 1])),
+                     "f"(__uint_as_float(r[4 * q + 2])), "f"(__uint_as_float(r[4 * q + 3]))
+                     : "memory");
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (col0 + j < n_limit) {
+        if (EPI == EPI_STORE_F32) crow[j] = __uint_as_float(r[j]);
+        else atomicAdd(crow + j, __uint_as_float(r[j]));
+      }
+  }
+}
 
+// 16-bit epilogue for one 32-column chunk of this warp's 32 rows: registers -> SWIZZLE_64B staging
+// tile (32 rows x 64 B) -> one TMA store (full 64-byte row segments, asynchronous, clipped at M / N).
+// `stage` is this warp's pair of 2 KiB buffers; at most one store is left in flight when a buffer is reused.
+__device__ __forceinline__ void store_chunk_tma(const uint32_t (&r)[32], int row0, int col0, const GemmParams& p,
+                                                int n_limit, const CUtensorMap* tmap_c, uint8_t* stage, int& buf,
+                                                int lane) {
+  // Nothing to write for this chunk (tile padding past N or M): leave the staging buffers alone — a
+  // skipped chunk commits no bulk group, so wait_group.read<1> below would not protect the buffer of
+  // the last real store from being overwritten (warp-uniform condition).
+  if (col0 >= n_limit || row0 >= p.M) return;
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  add_bias32(v, p, col0, n_limit);
+  if (lane == 0) ptx::tma_store_wait_read<1>();  // the buffer written two chunks ago has been read out
+  __syncwarp();
+  uint8_t* tile = stage + buf * 2048;
+  const uint32_t base = ptx::smem_u32(tile) + lane * 64;
+  const uint32_t sw = (lane >> 1) & 3;  // Swizzle<2,4,3>: 16-byte chunk index ^= address bits [7,9)
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint32_t a = base + ((q ^ sw) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack16(v[8 * q + 0], v[8 * q + 1], p.fmt)),
+                 "r"(pack16(v[8 * q + 2], v[8 * q + 3], p.fmt)), "r"(pack16(v[8 * q + 4], v[8 * q + 5], p.fmt)),
+                 "r"(pack16(v[8 * q + 6], v[8 * q + 7], p.fmt))
+                 : "memory");
+  }
+  ptx::fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+  __syncwarp();
+  if (lane == 0) {
+    ptx::tma_store_2d(tmap_c, tile, col0, row0);
+    ptx::tma_store_commit();
+  }
+  buf ^= 1;
+}
+
+template <bool PAIR>
+__device__ __forceinline__ void gemm_setup(uint64_t* full_bar, uint64_t* empty_bar, uint64_t* tfull_bar,
+                                           uint64_t* tempty_bar, uint32_t* tmem_slot, int stages, int warp, int lane) {
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < stages; ++s) {
+      ptx::mbar_init(&full_bar[s], PAIR ? 2 : 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tfull_bar[a], 1);
+      ptx::mbar_init(&tempty_bar[a], PAIR ? 8 : 4);  // one arrive per epilogue warp (of both CTAs)
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) {
+    if (PAIR) ptx::tmem_alloc_pair(tmem_slot, GEMM_TMEM_COLS);
+    else ptx::tmem_alloc(tmem_slot, GEMM_TMEM_COLS);
+  }
+  ptx::tc_fence_before();
+  if (PAIR) ptx::cluster_sync();  // barriers of both CTAs live before any remote arrive / multicast commit
+  else __syncthreads();
+  ptx::tc_fence_after();
+}
+
+template <bool PAIR>
+__device__ __forceinline__ void gemm_teardown(uint32_t tmem_base, int warp) {
+  ptx::tc_fence_before();
+  if (PAIR) ptx::cluster_sync();  // neither CTA may exit (or free TMEM) while its partner still uses it
+  else __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    if (PAIR) ptx::tmem_dealloc_pair(tmem_base, GEMM_TMEM_COLS);
+    else ptx::tmem_dealloc(tmem_base, GEMM_TMEM_COLS);
+  }
+}
+
+// MMA issue for one k-block (4 x K=16) + slot release
+template <bool PAIR, bool A_MN, bool B_MN>
+__device__ __forceinline__ void gemm_issue_kblock(uint32_t sa, uint32_t sb, uint32_t d_tmem, uint32_t idesc,
+                                                  bool first, uint64_t* empty_slot) {
+#pragma unroll
+  for (int kk = 0; kk < GEMM_BLOCK_K / GEMM_UMMA_K; ++kk) {
+    // K-major : advance 16 elements (32 B) inside the 128 B swizzle row
+    // MN-major: advance 16 k-rows of 128 B
+    const uint64_t da = A_MN ? ptx::make_smem_desc(sa + kk * 2048, GEMM_ATOM_BYTES, 1024)
+                             : ptx::make_smem_desc(sa + kk * 32, 16, 1024);
+    const uint64_t db = B_MN ? ptx::make_smem_desc(sb + kk * 2048, GEMM_ATOM_BYTES, 1024)
+                             : ptx::make_smem_desc(sb + kk * 32, 16, 1024);
+    const uint32_t acc = (!first || kk > 0) ? 1u : 0u;
+    if (PAIR) ptx::umma_f16_pair(d_tmem, da, db, idesc, acc);
+    else ptx::umma_f16(d_tmem, da, db, idesc, acc);
+  }
+  if (PAIR) ptx::umma_commit_pair(empty_slot, 0b11);  // frees this slot in BOTH CTAs once the MMAs retire
+  else ptx::umma_commit(empty_slot);
+}
+
+// Drain one accumulator (this warp's 32 rows x block_n columns) from TMEM and write it out.
+template <bool PAIR, int EPI>
+__device__ __forceinline__ void gemm_epilogue_tile(uint32_t t_row, int row0, int col_base, int n_limit, int block_n,
+                                                   const GemmParams& p, const CUtensorMap* tmap_c, uint8_t* stage,
+                                                   int& buf, uint64_t* tempty_slot, int lane) {
+  const int chunks = block_n >> 5;
+#pragma unroll 1
+  for (int c = 0; c < chunks; ++c) {
+    uint32_t r[32];
+    ptx::tmem_ld_32x32(t_row + c * 32, r);
+    ptx::tmem_ld_wait();
+    if (c == chunks - 1) {
+      // all of this warp's TMEM reads are done: hand the accumulator back to the MMA thread
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (PAIR) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(tempty_slot), 0));
+        else ptx::mbar_arrive(tempty_slot);
+      }
+    }
+    const int col0 = col_base + c * 32;
+    if (EPI == EPI_STORE16) store_chunk_tma(r, row0, col0, p, n_limit, tmap_c, stage, buf, lane);
+    else store_chunk_f32<EPI>(r, row0 + lane, col0, p, n_limit);
+  }
+}
+
+template <bool PAIR, bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint8_t* epi_smem = smem + GEMM_RING_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + GEMM_EPI_BYTES);
+  uint64_t* empty_bar = full_bar + GEMM_MAX_STAGES;
+  uint64_t* tfull_bar = empty_bar + GEMM_MAX_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0;  // 0 = leader
+  const int block_n = p.block_n;
+  const int b_rows = PAIR ? block_n / 2 : block_n;  // B rows (N columns) this CTA stages
+  const int stage_bytes = GEMM_A_BYTES + b_rows * GEMM_BLOCK_K * 2;
+  const int stages = p.stages;
+  const int rows_per_tile = PAIR ? 2 * GEMM_BLOCK_M : GEMM_BLOCK_M;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_a);
     ptx::prefetch_tmap(&tmap_b);
+    if (EPI == EPI_STORE16) ptx::prefetch_tmap(&tmap_c);
   }
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&empty_bar[s], 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      ptx::mbar_init(&tfull_bar[a], 1);
-      ptx::mbar_init(&tempty_bar[a], 4);  // one arrive per epilogue warp
-    }
-    ptx::fence_mbar_init();
-  }
-  if (warp == 2) ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
+  gemm_setup<PAIR>(full_bar, empty_bar, tfull_bar, tempty_bar, tmem_slot, stages, warp, lane);
   const uint32_t tmem_base = *tmem_slot;
 
+  const int workers = PAIR ? (gridDim.x >> 1) : gridDim.x;
+  const int worker = PAIR ? (blockIdx.x >> 1) : blockIdx.x;
   const int total = p.m_tiles * p.n_tiles * p.splits;
 
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
-    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+    for (int w = worker; w < total; w += workers) {
       const int split = w % p.splits;
       const int tile = w / p.splits;
       const int n_idx = tile % p.n_tiles;
       const int m_idx = tile / p.n_tiles;
       const int kb0 = static_cast<int>(static_cast<int64_t>(split) * p.k_blocks / p.splits);
       const int kb1 = static_cast<int>(static_cast<int64_t>(split + 1) * p.k_blocks / p.splits);
+      const int m0 = m_idx * rows_per_tile + static_cast<int>(rank) * GEMM_BLOCK_M;
+      const int n0 = n_idx * block_n + static_cast<int>(rank) * b_rows;
       for (int kb = kb0; kb < kb1; ++kb) {
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-        ptx::mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-        uint8_t* sa = smem + stage * STAGE_BYTES;
+        uint8_t* sa = smem + stage * stage_bytes;
         uint8_t* sb = sa + GEMM_A_BYTES;
-        if (!A_MN) {
-          ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * GEMM_BLOCK_K, m_idx * GEMM_BLOCK_M);
-        } else {
+        if (PAIR) {
+          const uint32_t full_leader = ptx::mapa(ptx::smem_u32(&full_bar[stage]), 0);
+          ptx::mbar_expect_tx_cluster(full_leader, stage_bytes);
+          if (!A_MN) {
+            ptx::tma_load_2d_pair(sa, &tmap_a, full_leader, kb * GEMM_BLOCK_K, m0);
+          } else {
 #pragma unroll
-          for (int j = 0; j < GEMM_BLOCK_M / 64; ++j)
-            ptx::tma_load_2d(sa + j * GEMM_ATOM_BYTES, &tmap_a, &full_bar[stage],
-                             m_idx * GEMM_BLOCK_M + j * 64, kb * GEMM_BLOCK_K);
-        }
-        if (!B_MN) {
-          ptx::tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * GEMM_BLOCK_K, n_idx * BLOCK_N);
+            for (int j = 0; j < GEMM_BLOCK_M / 64; ++j)
+              ptx::tma_load_2d_pair(sa + j * GEMM_ATOM_BYTES, &tmap_a, full_leader, m0 + j * 64, kb * GEMM_BLOCK_K);
+          }
+          if (!B_MN) {
+            ptx::tma_load_2d_pair(sb, &tmap_b, full_leader, kb * GEMM_BLOCK_K, n0);
+          } else {
+            for (int j = 0; j < b_rows / 64; ++j)
+              ptx::tma_load_2d_pair(sb + j * GEMM_ATOM_BYTES, &tmap_b, full_leader, n0 + j * 64, kb * GEMM_BLOCK_K);
+          }
         } else {
+          ptx::mbar_expect_tx(&full_bar[stage], stage_bytes);
+          if (!A_MN) {
+            ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * GEMM_BLOCK_K, m0);
+          } else {
 #pragma unroll
-          for (int j = 0; j < BLOCK_N / 64; ++j)
-            ptx::tma_load_2d(sb + j * GEMM_ATOM_BYTES, &tmap_b, &full_bar[stage],
-                             n_idx * BLOCK_N + j * 64, kb * GEMM_BLOCK_K);
+            for (int j = 0; j < GEMM_BLOCK_M / 64; ++j)
+              ptx::tma_load_2d(sa + j * GEMM_ATOM_BYTES, &tmap_a, &full_bar[stage], m0 + j * 64, kb * GEMM_BLOCK_K);
+          }
+          if (!B_MN) {
+            ptx::tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * GEMM_BLOCK_K, n0);
+          } else {
+            for (int j = 0; j < b_rows / 64; ++j)
+              ptx::tma_load_2d(sb + j * GEMM_ATOM_BYTES, &tmap_b, &full_bar[stage], n0 + j * 64, kb * GEMM_BLOCK_K);
+          }
         }
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == stages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // -------------------------------------------------------------- MMA issuer
-    const uint32_t idesc = ptx::make_idesc_f16(p.fmt, GEMM_BLOCK_M, BLOCK_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
+  } else if (warp == 1 && lane == 0 && rank == 0) {
+    // ------------------------------------------------- MMA issuer (leader CTA only for a pair)
+    const uint32_t idesc = ptx::make_idesc_f16(p.fmt, rows_per_tile, block_n, A_MN ? 1 : 0, B_MN ? 1 : 0);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+    for (int w = worker; w < total; w += workers) {
       const int split = w % p.splits;
       const int kb0 = static_cast<int>(static_cast<int64_t>(split) * p.k_blocks / p.splits);
       const int kb1 = static_cast<int>(static_cast<int64_t>(split + 1) * p.k_blocks / p.splits);
       ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       ptx::tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      const uint32_t d_tmem = tmem_base + acc * 256;
       for (int kb = kb0; kb < kb1; ++kb) {
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after();
-        const uint32_t sa = ptx::smem_u32(smem + stage * STAGE_BYTES);
-        const uint32_t sb = sa + GEMM_A_BYTES;
-#pragma unroll
-        for (int kk = 0; kk < GEMM_BLOCK_K / GEMM_UMMA_K; ++kk) {
-          // K-major : advance 16 elements (32 B) inside the 128 B swizzle row
-          // MN-major: advance 16 k-rows of 128 B
-          const uint64_t da = A_MN ? ptx::make_smem_desc(sa + kk * 2048, GEMM_ATOM_BYTES, 1024)
-                                   : ptx::make_smem_desc(sa + kk * 32, 16, 1024);
-          const uint64_t db = B_MN ? ptx::make_smem_desc(sb + kk * 2048, GEMM_ATOM_BYTES, 1024)
-                                   : ptx::make_smem_desc(sb + kk * 32, 16, 1024);
-          ptx::umma_f16(d_tmem, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
-        }
-        ptx::umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        const uint32_t sa = ptx::smem_u32(smem + stage * stage_bytes);
+        gemm_issue_kblock<PAIR, A_MN, B_MN>(sa, sa + GEMM_A_BYTES, d_tmem, idesc, kb == kb0, &empty_bar[stage]);
+        if (++stage == stages) { stage = 0; phase ^= 1; }
       }
-      ptx::umma_commit(&tfull_bar[acc]);  // accumulator complete
+      if (PAIR) ptx::umma_commit_pair(&tfull_bar[acc], 0b11);  // accumulator halves complete in both CTAs
+      else ptx::umma_commit(&tfull_bar[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue
     const int ew = warp - 4;  // == warp % 4 -> TMEM lanes [32*ew, 32*ew + 32)
+    uint8_t* stage_buf = epi_smem + ew * 4096;
+    int buf = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+    for (int w = worker; w < total; w += workers) {
       const int tile = w / p.splits;
       const int n_idx = tile % p.n_tiles;
       const int m_idx = tile / p.n_tiles;
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tc_fence_after();
-      const int row = m_idx * GEMM_BLOCK_M + ew * 32 + lane;
-      const uint32_t t_row = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(ew * 32) << 16);
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(t_row + c * 32, r);
-        ptx::tmem_ld_wait();
-        if (c == BLOCK_N / 32 - 1) {
-          // all of this warp's TMEM reads are done: hand the accumulator back to the MMA warp
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
-        }
-        store_chunk<EPI>(r, row, n_idx * BLOCK_N + c * 32, p);
-      }
+      const int row0 = m_idx * rows_per_tile + static_cast<int>(rank) * GEMM_BLOCK_M + ew * 32;
+      const uint32_t t_row = tmem_base + acc * 256 + (static_cast<uint32_t>(ew * 32) << 16);
+      gemm_epilogue_tile<PAIR, EPI>(t_row, row0, n_idx * block_n, p.N, block_n, p, &tmap_c, stage_buf, buf,
+                                    &tempty_bar[acc], lane);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (EPI == EPI_STORE16 && lane == 0) ptx::tma_store_wait_read<0>();  // staging smem must outlive the stores
   }
 
-  ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
-  }
+  gemm_teardown<PAIR>(tmem_base, warp);
 }
 
 }  // namespace lyco

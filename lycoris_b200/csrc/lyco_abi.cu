@@ -11,7 +11,6 @@
 
 #include "../../include/lyco_b200.h"
 #include "conv_sm100.cuh"
-#include "gemm_pair_sm100.cuh"
 #include "gemm_sm100.cuh"
 #include "weight_kernels.cuh"
 
@@ -134,106 +133,87 @@ int make_tmap_im2col(CUtensorMap* m, const void* base, int Nb, int H, int W, int
   return 0;
 }
 
-template <int BN, int MODE, int EPI>
-int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const lyco::ConvParams& cp, int grid,
-                cudaStream_t stream) {
-  auto kern = lyco::conv_sm100_kernel<BN, MODE, EPI>;
-  static bool configured[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (!configured[dev & 63]) {
-    LYCO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   lyco::GemmCfg<BN>::SMEM_BYTES));
-    configured[dev & 63] = true;
-  }
-  kern<<<grid, lyco::GEMM_THREADS, lyco::GemmCfg<BN>::SMEM_BYTES, stream>>>(ta, tb, cp);
-  LYCO_CUDA(cudaGetLastError());
+// C tensor map for the TMA-store epilogue: [M rows, N inner] 16-bit, boxes of 32 rows x 32 columns, 64B swizzle
+int make_tmap_c(CUtensorMap* m, const void* base, uint64_t N, uint64_t M, uint64_t ld_elems) {
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return fail("cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t gdim[2] = {N, M};
+  cuuint64_t gstr[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail("cuTensorMapEncodeTiled (C) failed (%d): base=%p N=%llu M=%llu ld=%llu", static_cast<int>(r), base,
+                (unsigned long long)N, (unsigned long long)M, (unsigned long long)ld_elems);
+  return 0;
+}
+
+template <typename Kern, typename Params>
+int launch_persistent(Kern kern, bool pair, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+                      const Params& p, int grid, cudaStream_t stream) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(lyco::GEMM_THREADS);
+  cfg.dynamicSmemBytes = lyco::GEMM_SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = pair ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  LYCO_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, p));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
-int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const lyco::GemmParams& p, int grid,
-                cudaStream_t stream) {
-  auto kern = lyco::gemm_sm100_kernel<BN, A_MN, B_MN, EPI>;
-  static bool configured[64] = {};
+template <typename Kern>
+int ensure_smem(Kern kern, bool* configured) {
   int dev = 0;
   cudaGetDevice(&dev);
   if (!configured[dev & 63]) {
-    LYCO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   lyco::GemmCfg<BN>::SMEM_BYTES));
+    LYCO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lyco::GEMM_SMEM_BYTES));
     configured[dev & 63] = true;
   }
-  kern<<<grid, lyco::GEMM_THREADS, lyco::GemmCfg<BN>::SMEM_BYTES, stream>>>(ta, tb, p);
-  LYCO_CUDA(cudaGetLastError());
-  g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
-int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, const lyco::GemmParams& p, int grid,
-                     cudaStream_t stream) {
-  auto kern = lyco::gemm_pair_sm100_kernel<BN, A_MN, B_MN, EPI>;
+template <bool PAIR, bool A_MN, bool B_MN, int EPI>
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const lyco::GemmParams& p,
+                int grid, cudaStream_t stream) {
+  auto kern = lyco::gemm_sm100_kernel<PAIR, A_MN, B_MN, EPI>;
   static bool configured[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (!configured[dev & 63]) {
-    LYCO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   lyco::PairCfg<BN>::SMEM_BYTES));
-    configured[dev & 63] = true;
-  }
-  kern<<<grid, lyco::GEMM_THREADS, lyco::PairCfg<BN>::SMEM_BYTES, stream>>>(ta, tb, p);
-  LYCO_CUDA(cudaGetLastError());
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  return 0;
+  if (ensure_smem(kern, configured)) return 1;
+  return launch_persistent(kern, PAIR, ta, tb, tc, p, grid, stream);
 }
 
-template <int BN>
-int dispatch_gemm_pair(bool a_mn, bool b_mn, int epi, const CUtensorMap& ta, const CUtensorMap& tb,
-                       const lyco::GemmParams& p, int grid, cudaStream_t s) {
-  using namespace lyco;
-  if (!a_mn && !b_mn) {
-    if (epi == EPI_STORE16) return launch_gemm_pair<BN, false, false, EPI_STORE16>(ta, tb, p, grid, s);
-    if (epi == EPI_STORE_F32) return launch_gemm_pair<BN, false, false, EPI_STORE_F32>(ta, tb, p, grid, s);
-    return launch_gemm_pair<BN, false, false, EPI_ATOMIC_F32>(ta, tb, p, grid, s);
-  }
-  if (!a_mn && b_mn) {
-    if (epi == EPI_STORE16) return launch_gemm_pair<BN, false, true, EPI_STORE16>(ta, tb, p, grid, s);
-    if (epi == EPI_STORE_F32) return launch_gemm_pair<BN, false, true, EPI_STORE_F32>(ta, tb, p, grid, s);
-    return launch_gemm_pair<BN, false, true, EPI_ATOMIC_F32>(ta, tb, p, grid, s);
-  }
-  if (a_mn && b_mn) {
-    if (epi == EPI_STORE16) return launch_gemm_pair<BN, true, true, EPI_STORE16>(ta, tb, p, grid, s);
-    if (epi == EPI_STORE_F32) return launch_gemm_pair<BN, true, true, EPI_STORE_F32>(ta, tb, p, grid, s);
-    return launch_gemm_pair<BN, true, true, EPI_ATOMIC_F32>(ta, tb, p, grid, s);
-  }
-  if (epi == EPI_STORE16) return launch_gemm_pair<BN, true, false, EPI_STORE16>(ta, tb, p, grid, s);
-  if (epi == EPI_STORE_F32) return launch_gemm_pair<BN, true, false, EPI_STORE_F32>(ta, tb, p, grid, s);
-  return launch_gemm_pair<BN, true, false, EPI_ATOMIC_F32>(ta, tb, p, grid, s);
-}
-
-template <int BN>
-int dispatch_gemm(bool a_mn, bool b_mn, int epi, const CUtensorMap& ta, const CUtensorMap& tb,
+template <bool PAIR>
+int dispatch_gemm(bool a_mn, bool b_mn, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
                   const lyco::GemmParams& p, int grid, cudaStream_t s) {
   using namespace lyco;
-  if (!a_mn && !b_mn) {
-    if (epi == EPI_STORE16) return launch_gemm<BN, false, false, EPI_STORE16>(ta, tb, p, grid, s);
-    if (epi == EPI_STORE_F32) return launch_gemm<BN, false, false, EPI_STORE_F32>(ta, tb, p, grid, s);
-    return launch_gemm<BN, false, false, EPI_ATOMIC_F32>(ta, tb, p, grid, s);
-  }
-  if (!a_mn && b_mn) {
-    if (epi == EPI_STORE16) return launch_gemm<BN, false, true, EPI_STORE16>(ta, tb, p, grid, s);
-    if (epi == EPI_STORE_F32) return launch_gemm<BN, false, true, EPI_STORE_F32>(ta, tb, p, grid, s);
-    return launch_gemm<BN, false, true, EPI_ATOMIC_F32>(ta, tb, p, grid, s);
-  }
-  if (a_mn && b_mn) {
-    if (epi == EPI_STORE16) return launch_gemm<BN, true, true, EPI_STORE16>(ta, tb, p, grid, s);
-    if (epi == EPI_STORE_F32) return launch_gemm<BN, true, true, EPI_STORE_F32>(ta, tb, p, grid, s);
-    return launch_gemm<BN, true, true, EPI_ATOMIC_F32>(ta, tb, p, grid, s);
-  }
-  if (epi == EPI_STORE16) return launch_gemm<BN, true, false, EPI_STORE16>(ta, tb, p, grid, s);
-  if (epi == EPI_STORE_F32) return launch_gemm<BN, true, false, EPI_STORE_F32>(ta, tb, p, grid, s);
-  return launch_gemm<BN, true, false, EPI_ATOMIC_F32>(ta, tb, p, grid, s);
+#define LYCO_EPI(AM, BM)                                                                             \
+  do {                                                                                               \
+    if (epi == EPI_STORE16) return launch_gemm<PAIR, AM, BM, EPI_STORE16>(ta, tb, tc, p, grid, s);   \
+    if (epi == EPI_STORE_F32) return launch_gemm<PAIR, AM, BM, EPI_STORE_F32>(ta, tb, tc, p, grid, s); \
+    return launch_gemm<PAIR, AM, BM, EPI_ATOMIC_F32>(ta, tb, tc, p, grid, s);                        \
+  } while (0)
+  if (!a_mn && !b_mn) LYCO_EPI(false, false);
+  if (!a_mn && b_mn) LYCO_EPI(false, true);
+  if (a_mn && b_mn) LYCO_EPI(true, true);
+  LYCO_EPI(true, false);
+#undef LYCO_EPI
+}
+
+template <int MODE, int EPI>
+int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const lyco::ConvParams& cp,
+                int grid, cudaStream_t stream) {
+  auto kern = lyco::conv_sm100_kernel<MODE, EPI>;
+  static bool configured[64] = {};
+  if (ensure_smem(kern, configured)) return 1;
+  return launch_persistent(kern, false, ta, tb, tc, cp, grid, stream);
 }
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
@@ -248,16 +228,13 @@ struct TileChoice {
 
 inline double tile_cost(bool pair, int bn) {
   const double mma = bn, feed = 0.85 * (128 + (pair ? bn / 2 : bn));
-  return mma > feed ? mma : feed;
+  return (mma > feed ? mma : feed) + 12.0;  // + fixed per-tile overhead (pipeline fill, epilogue hand-off)
 }
 
-inline int force_choice(TileChoice* c) {
-  // LYCO_GEMM_FORCE=pair256|pair128|single256|single128|single64 (experiments / tests)
-  static const char* env = getenv("LYCO_GEMM_FORCE");
-  if (!env || !*env) return 0;
-  if (!strncmp(env, "pair", 4)) { c->pair = true; c->bn = atoi(env + 4); return c->bn == 256 || c->bn == 128; }
-  if (!strncmp(env, "single", 6)) { c->pair = false; c->bn = atoi(env + 6); return c->bn == 256 || c->bn == 128 || c->bn == 64; }
-  return 0;
+inline int stages_for(bool pair, int bn) {
+  const int stage_bytes = lyco::GEMM_A_BYTES + (pair ? bn / 2 : bn) * lyco::GEMM_BLOCK_K * 2;
+  const int s = lyco::GEMM_RING_BYTES / stage_bytes;
+  return s > lyco::GEMM_MAX_STAGES ? lyco::GEMM_MAX_STAGES : s;
 }
 
 inline bool pair_enabled() {
@@ -266,19 +243,41 @@ inline bool pair_enabled() {
   return on;
 }
 
-TileChoice pick_tile(int M, int N, int sms, int splits_hint) {
-  TileChoice best{false, 64};
-  if (force_choice(&best)) return best;
+inline bool tile_valid(bool pair, int bn, bool b_mn) {
+  if (bn < 32 || bn > 256 || bn % 32) return false;
+  if (b_mn) return pair ? (bn % 128 == 0) : (bn % 64 == 0);  // MN-major B comes in 64-column atoms per CTA
+  return !pair || bn >= 64;
+}
+
+inline int force_choice(TileChoice* c, bool b_mn) {
+  // LYCO_GEMM_FORCE=pair<bn>|single<bn> (experiments / tests)
+  static const char* env = getenv("LYCO_GEMM_FORCE");
+  if (!env || !*env) return 0;
+  TileChoice t;
+  if (!strncmp(env, "pair", 4)) { t.pair = true; t.bn = atoi(env + 4); }
+  else if (!strncmp(env, "single", 6)) { t.pair = false; t.bn = atoi(env + 6); }
+  else return 0;
+  if (!tile_valid(t.pair, t.bn, b_mn)) return 0;
+  *c = t;
+  return 1;
+}
+
+// Minimise (waves of tiles) x (cost of one tile step); ties go to the larger tile.
+TileChoice pick_tile(int M, int N, int sms, int splits, bool b_mn) {
+  TileChoice best{false, b_mn ? 64 : 32};
+  if (force_choice(&best, b_mn)) return best;
   double best_cost = 1e30;
-  const TileChoice cands[5] = {{true, 256}, {true, 128}, {false, 256}, {false, 128}, {false, 64}};
-  const int sp = splits_hint > 0 ? splits_hint : 1;
-  for (const TileChoice& c : cands) {
-    if (c.pair && (M <= 128 || !pair_enabled())) continue;
-    const long tiles = static_cast<long>(cdiv(M, c.pair ? 256 : 128)) * cdiv(N, c.bn) * sp;
-    const long slots = c.pair ? sms / 2 : sms;
-    const long waves = (tiles + slots - 1) / slots;
-    const double cost = waves * tile_cost(c.pair, c.bn);
-    if (cost < best_cost * 0.999) { best_cost = cost; best = c; }
+  for (int pair = 1; pair >= 0; --pair) {
+    if (pair && (M <= 128 || !pair_enabled())) continue;
+    for (int bn = 256; bn >= 32; bn -= 32) {
+      if (!tile_valid(pair, bn, b_mn)) continue;
+      if (bn > 32 && bn - 32 >= N) continue;  // narrower tile already covers N
+      const long tiles = static_cast<long>(cdiv(M, pair ? 256 : 128)) * cdiv(N, bn) * (splits > 0 ? splits : 1);
+      const long slots = pair ? sms / 2 : sms;
+      const long waves = (tiles + slots - 1) / slots;
+      const double cost = waves * tile_cost(pair, bn);
+      if (cost < best_cost * 0.995) { best_cost = cost; best = TileChoice{pair != 0, bn}; }
+    }
   }
   return best;
 }
@@ -363,30 +362,40 @@ int lyco_gemm(const void* A, int a_mn_major, int64_t lda, const void* B, int b_m
   if (device_info(&di)) return 1;
 
   const int k_blocks = cdiv(K, lyco::GEMM_BLOCK_K);
+  const bool a_mn = a_mn_major != 0, b_mn = b_mn_major != 0;
   int splits = 1;
-  TileChoice tc = pick_tile(M, N, di.sms, 1);
+  TileChoice tc = pick_tile(M, N, di.sms, 1, b_mn);
   if (c_dtype == LYCO_F32) {
-    // wgrad-like: few output tiles, long reduction -> largest tile, split the reduction across CTAs
+    // wgrad-like: few output tiles, long reduction -> widest tile, split the reduction across CTAs
     TileChoice forced;
-    if (force_choice(&forced)) tc = forced;
-    else { tc.pair = M > 128 && pair_enabled(); tc.bn = N >= 256 ? 256 : (N >= 128 ? 128 : 64); if (tc.bn == 64) tc.pair = false; }
+    if (force_choice(&forced, b_mn)) {
+      tc = forced;
+    } else {
+      tc.pair = M > 128 && pair_enabled();
+      tc.bn = 256;
+      while (tc.bn > 32 && tc.bn - (b_mn ? (tc.pair ? 128 : 64) : 32) >= N) tc.bn -= b_mn ? (tc.pair ? 128 : 64) : 32;
+      if (!tile_valid(tc.pair, tc.bn, b_mn)) { tc.pair = false; tc.bn = b_mn ? 64 : 32; }
+    }
     const long tiles = static_cast<long>(cdiv(M, tc.pair ? 256 : 128)) * cdiv(N, tc.bn);
     splits = split_k > 0 ? split_k : pick_splits(tiles, k_blocks, tc.pair ? di.sms / 2 : di.sms);
     if (splits > k_blocks) splits = k_blocks;
   }
   const int bn = tc.bn;
-  const int m_tiles = cdiv(M, tc.pair ? lyco::PAIR_BLOCK_M : lyco::GEMM_BLOCK_M);
+  const int m_tiles = cdiv(M, tc.pair ? 256 : 128);
   const int n_tiles = cdiv(N, bn);
 
-  CUtensorMap ta, tb;
-  if (!a_mn_major) { if (make_tmap(&ta, A, K, M, lda, 64, 128)) return 1; }
-  else             { if (make_tmap(&ta, A, M, K, lda, 64, 64)) return 1; }
-  if (!b_mn_major) { if (make_tmap(&tb, B, K, N, ldb, 64, tc.pair ? bn / 2 : bn)) return 1; }
-  else             { if (make_tmap(&tb, B, N, K, ldb, 64, 64)) return 1; }
+  CUtensorMap ta, tb, tcm;
+  memset(&tcm, 0, sizeof(tcm));
+  if (!a_mn) { if (make_tmap(&ta, A, K, M, lda, 64, 128)) return 1; }
+  else       { if (make_tmap(&ta, A, M, K, lda, 64, 64)) return 1; }
+  if (!b_mn) { if (make_tmap(&tb, B, K, N, ldb, 64, tc.pair ? bn / 2 : bn)) return 1; }
+  else       { if (make_tmap(&tb, B, N, K, ldb, 64, 64)) return 1; }
+  if (c_dtype != LYCO_F32) { if (make_tmap_c(&tcm, C, N, M, ldc)) return 1; }
 
   lyco::GemmParams p;
   p.C = C; p.bias = bias; p.ldc = ldc; p.M = M; p.N = N; p.K = K;
   p.m_tiles = m_tiles; p.n_tiles = n_tiles; p.splits = splits; p.k_blocks = k_blocks;
+  p.block_n = bn; p.stages = stages_for(tc.pair, bn);
   p.fmt = (ab_dtype == LYCO_BF16) ? 1 : 0;
   p.bias_dtype = bias_dtype;
 
@@ -399,17 +408,13 @@ int lyco_gemm(const void* A, int a_mn_major, int64_t lda, const void* B, int b_m
     }
   }
   const long total = static_cast<long>(m_tiles) * n_tiles * splits;
-  const bool a_mn = a_mn_major != 0, b_mn = b_mn_major != 0;
   if (tc.pair) {
     const long slots = di.sms / 2;
     const int grid = 2 * static_cast<int>(total < slots ? total : slots);
-    if (bn == 256) return dispatch_gemm_pair<256>(a_mn, b_mn, epi, ta, tb, p, grid, stream);
-    return dispatch_gemm_pair<128>(a_mn, b_mn, epi, ta, tb, p, grid, stream);
+    return dispatch_gemm<true>(a_mn, b_mn, epi, ta, tb, tcm, p, grid, stream);
   }
   const int grid = static_cast<int>(total < di.sms ? total : di.sms);
-  if (bn == 256) return dispatch_gemm<256>(a_mn, b_mn, epi, ta, tb, p, grid, stream);
-  if (bn == 128) return dispatch_gemm<128>(a_mn, b_mn, epi, ta, tb, p, grid, stream);
-  return dispatch_gemm<64>(a_mn, b_mn, epi, ta, tb, p, grid, stream);
+  return dispatch_gemm<false>(a_mn, b_mn, epi, ta, tb, tcm, p, grid, stream);
 }
 
 int lyco_conv2d_fprop(const void* X, const void* Wk, void* Y, const void* bias, int bias_dtype, int Nb, int H,
@@ -429,32 +434,34 @@ int lyco_conv2d_fprop(const void* X, const void* Wk, void* Y, const void* bias, 
   const int64_t M64 = static_cast<int64_t>(Nb) * P * Q;
   if (M64 > (1ll << 30)) return fail("lyco_conv2d_fprop: too many output pixels");
   const int M = static_cast<int>(M64), K = R * S * C;
-  TileChoice tc{false, 64};
+  TileChoice tc = pick_tile(M, O, di.sms, 1, false);
+  tc.pair = false;  // the im2col producer is single-CTA for now
   {
     double best = 1e30;
-    const int cands[3] = {256, 128, 64};
-    for (int bn : cands) {
+    for (int bn = 256; bn >= 32; bn -= 32) {
+      if (bn > 32 && bn - 32 >= O) continue;
       const long tiles = static_cast<long>(cdiv(M, 128)) * cdiv(O, bn);
       const long waves = (tiles + di.sms - 1) / di.sms;
       const double cost = waves * tile_cost(false, bn);
-      if (cost < best * 0.999) { best = cost; tc.bn = bn; }
+      if (cost < best * 0.995) { best = cost; tc.bn = bn; }
     }
   }
+  if (const char* e = getenv("LYCO_CONV_BN")) { const int f = atoi(e); if (f >= 32 && f <= 256 && f % 32 == 0) tc.bn = f; }
   const int bn = tc.bn;
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tcm;
   if (make_tmap_im2col(&ta, X, Nb, H, W, C, R, S, pad_h, pad_w, stride, 128)) return 1;
   if (make_tmap(&tb, Wk, K, O, K, 64, bn)) return 1;
+  if (make_tmap_c(&tcm, Y, O, M, O)) return 1;
   lyco::ConvParams cp;
   cp.g.C = Y; cp.g.bias = bias; cp.g.ldc = O; cp.g.M = M; cp.g.N = O; cp.g.K = K;
   cp.g.m_tiles = cdiv(M, 128); cp.g.n_tiles = cdiv(O, bn); cp.g.splits = 1; cp.g.k_blocks = R * S * (C / 64);
+  cp.g.block_n = bn; cp.g.stages = stages_for(false, bn);
   cp.g.fmt = (dtype == LYCO_BF16) ? 1 : 0; cp.g.bias_dtype = bias_dtype;
   cp.PQ = P * Q; cp.Q = Q; cp.C = C; cp.CB = C / 64; cp.S = S; cp.stride = stride;
   cp.low_w = -pad_w; cp.low_h = -pad_h; cp.tiles_per_tap = 1;
   const long total = static_cast<long>(cp.g.m_tiles) * cp.g.n_tiles;
   const int grid = static_cast<int>(total < di.sms ? total : di.sms);
-  if (bn == 256) return launch_conv<256, lyco::MODE_FPROP, lyco::EPI_STORE16>(ta, tb, cp, grid, stream);
-  if (bn == 128) return launch_conv<128, lyco::MODE_FPROP, lyco::EPI_STORE16>(ta, tb, cp, grid, stream);
-  return launch_conv<64, lyco::MODE_FPROP, lyco::EPI_STORE16>(ta, tb, cp, grid, stream);
+  return launch_conv<lyco::MODE_FPROP, lyco::EPI_STORE16>(ta, tb, tcm, cp, grid, stream);
 }
 
 int lyco_conv2d_wgrad(const void* X, const void* dY, float* dW, int Nb, int H, int W, int C, int O, int R, int S,
@@ -470,14 +477,13 @@ int lyco_conv2d_wgrad(const void* X, const void* dY, float* dW, int Nb, int H, i
   const int64_t M64 = static_cast<int64_t>(Nb) * P * Q;
   if (M64 > (1ll << 30)) return fail("lyco_conv2d_wgrad: too many output pixels");
   const int Mpix = static_cast<int>(M64);
-  // N tile: the widest of 256/128/64 that wastes the least padding inside one filter tap
+  // N tile (64-column im2col atoms): least padding inside one filter tap per unit of tile cost
   int bn = 64;
   double best = 1e30;
-  const int cands[3] = {256, 128, 64};
-  for (int c : cands) {
+  for (int c = 256; c >= 64; c -= 64) {
     const double waste = static_cast<double>(cdiv(C, c) * c) / C;  // >= 1
     const double cost = waste * tile_cost(false, c) / c;
-    if (cost < best * 0.999) { best = cost; bn = c; }
+    if (cost < best * 0.995) { best = cost; bn = c; }
   }
   const int tiles_per_tap = cdiv(C, bn);
   const int taps = R * S;
@@ -485,27 +491,23 @@ int lyco_conv2d_wgrad(const void* X, const void* dY, float* dW, int Nb, int H, i
   const long tiles = static_cast<long>(cdiv(O, 128)) * taps * tiles_per_tap;
   int splits = split_k > 0 ? split_k : pick_splits(tiles, k_blocks, di.sms);
   if (splits > k_blocks) splits = k_blocks;
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tcm;
+  memset(&tcm, 0, sizeof(tcm));
   if (make_tmap(&ta, dY, O, Mpix, O, 64, 64)) return 1;  // dY [Mpix, O] consumed MN-major
   if (make_tmap_im2col(&tb, X, Nb, H, W, C, R, S, pad_h, pad_w, stride, 64)) return 1;
   lyco::ConvParams cp;
   const int ldw = taps * C;
   cp.g.C = dW; cp.g.bias = nullptr; cp.g.ldc = ldw; cp.g.M = O; cp.g.N = ldw; cp.g.K = Mpix;
   cp.g.m_tiles = cdiv(O, 128); cp.g.n_tiles = taps * tiles_per_tap; cp.g.splits = splits; cp.g.k_blocks = k_blocks;
+  cp.g.block_n = bn; cp.g.stages = stages_for(false, bn);
   cp.g.fmt = (dtype == LYCO_BF16) ? 1 : 0; cp.g.bias_dtype = 0;
   cp.PQ = P * Q; cp.Q = Q; cp.C = C; cp.CB = C / 64; cp.S = S; cp.stride = stride;
   cp.low_w = -pad_w; cp.low_h = -pad_h; cp.tiles_per_tap = tiles_per_tap;
   if (splits > 1) LYCO_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * static_cast<size_t>(O) * ldw, stream));
   const long total = tiles * splits;
   const int grid = static_cast<int>(total < di.sms ? total : di.sms);
-  if (splits > 1) {
-    if (bn == 256) return launch_conv<256, lyco::MODE_WGRAD, lyco::EPI_ATOMIC_F32>(ta, tb, cp, grid, stream);
-    if (bn == 128) return launch_conv<128, lyco::MODE_WGRAD, lyco::EPI_ATOMIC_F32>(ta, tb, cp, grid, stream);
-    return launch_conv<64, lyco::MODE_WGRAD, lyco::EPI_ATOMIC_F32>(ta, tb, cp, grid, stream);
-  }
-  if (bn == 256) return launch_conv<256, lyco::MODE_WGRAD, lyco::EPI_STORE_F32>(ta, tb, cp, grid, stream);
-  if (bn == 128) return launch_conv<128, lyco::MODE_WGRAD, lyco::EPI_STORE_F32>(ta, tb, cp, grid, stream);
-  return launch_conv<64, lyco::MODE_WGRAD, lyco::EPI_STORE_F32>(ta, tb, cp, grid, stream);
+  if (splits > 1) return launch_conv<lyco::MODE_WGRAD, lyco::EPI_ATOMIC_F32>(ta, tb, tcm, cp, grid, stream);
+  return launch_conv<lyco::MODE_WGRAD, lyco::EPI_STORE_F32>(ta, tb, tcm, cp, grid, stream);
 }
 
 int lyco_merge_weight(const lyco_delta_desc_t* d, const void* W, void* W_out, void* stream_) {

@@ -100,21 +100,26 @@ def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, out_dtype=None, split_k=0, 
 
 
 def conv2d_supported(x, weight_shape, stride, padding, dilation, groups) -> bool:
-    """The implicit-GEMM kernels take NHWC (channels_last) activations, C % 64 == 0, O % 8 == 0."""
+    """Geometry the implicit-GEMM kernels cover: 2-D, dilation 1, groups 1, C % 64 == 0, O % 8 == 0.
+    (Activations must be NHWC; callers convert NCHW tensors with one transpose pass.)"""
     if x.dim() != 4 or len(weight_shape) != 4 or x.dtype not in (torch.bfloat16, torch.float16):
         return False
     O, C, R, S = weight_shape
     if groups != 1 or tuple(dilation) != (1, 1) or stride[0] != stride[1] or not (1 <= stride[0] <= 8):
         return False
-    if C % 64 or O % 8 or x.data_ptr() % 16:
-        return False
-    return x.is_contiguous(memory_format=torch.channels_last)
+    return C % 64 == 0 and O % 8 == 0
+
+
+def as_nhwc(x):
+    """channels_last view of ``x`` (a transpose copy only if it is not already NHWC in memory)."""
+    return x if x.is_contiguous(memory_format=torch.channels_last) else x.contiguous(memory_format=torch.channels_last)
 
 
 def conv2d_fprop(x, wk, bias, R, S, pad, stride):
     """``x``: [Nb, C, H, W] in channels_last storage; ``wk``: [O, R*S*C] (filter as [O,R,S,C]).
     Returns y [Nb, O, P, Q] in channels_last storage."""
     _require_cuda(x, wk, bias)
+    x = as_nhwc(x)
     Nb, C, H, W = x.shape
     O = wk.shape[0]
     P = (H + 2 * pad[0] - R) // stride + 1
@@ -130,6 +135,7 @@ def conv2d_fprop(x, wk, bias, R, S, pad, stride):
 def conv2d_wgrad(x, dy, R, S, pad, stride, split_k=0):
     """fp32 [O, R*S*C] weight gradient from channels_last ``x`` [Nb,C,H,W] and ``dy`` [Nb,O,P,Q]."""
     _require_cuda(x, dy)
+    x, dy = as_nhwc(x), as_nhwc(dy)
     Nb, C, H, W = x.shape
     O = dy.shape[1]
     dw = torch.empty((O, R * S * C), device=x.device, dtype=torch.float32)
@@ -191,6 +197,6 @@ def factor_grads(desc: DeltaDesc, dW: torch.Tensor, W, shapes):
 
 
 __all__ = [
-    "gemm", "gemm_supported", "conv2d_supported", "conv2d_fprop", "conv2d_wgrad", "make_desc", "merge_weight", "factor_grads", "dtype_code",
+    "gemm", "gemm_supported", "conv2d_supported", "as_nhwc", "conv2d_fprop", "conv2d_wgrad", "make_desc", "merge_weight", "factor_grads", "dtype_code",
     "ALGO_LOCON", "ALGO_LOHA", "ALGO_LOKR", "ALGO_IA3", "ALGO_DYLORA", "BF16", "F16", "F32",
 ]

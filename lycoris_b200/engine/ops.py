@@ -121,7 +121,7 @@ def _conv_backward(dy, x, w, cp, need_x, need_w):
     if _conv_engine_ok(x, w, cp):
         O, C, R, S = w.shape
         st, pad = cp["stride"][0], cp["padding"]
-        dyc = dy.contiguous(memory_format=torch.channels_last)
+        dyc = K.as_nhwc(dy)
         dx = dw = None
         if need_x:
             if st == 1 and O % 64 == 0 and C % 8 == 0 and pad[0] <= R - 1 and pad[1] <= S - 1:
@@ -167,6 +167,8 @@ class _AdapterContraction(torch.autograd.Function):
                 x2 = x2.contiguous()
             y = _dense_nt(x2, Wm, bias).view(*x.shape[:-1], out_dim)
         else:
+            if _conv_engine_ok(x, Wm, conv):
+                x = K.as_nhwc(x)  # one transpose at most; the NHWC copy is what backward's wgrad reads again
             y = _conv_forward(x, Wm, bias, conv)
         ctx.save_for_backward(x, W, Wm, *factors)
         ctx.spec, ctx.conv, ctx.ac_dtype = spec, conv, ac_dtype
@@ -221,6 +223,8 @@ class _MergedContraction(torch.autograd.Function):
                 x2 = x2.contiguous()
             y = _dense_nt(x2, Wm.contiguous(), bias).view(*x.shape[:-1], Wm.shape[0])
         else:
+            if _conv_engine_ok(x, Wm, conv):
+                x = K.as_nhwc(x)
             y = _conv_forward(x, Wm, bias, conv)
         ctx.save_for_backward(x, Wm)
         ctx.conv = conv

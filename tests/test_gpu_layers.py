@@ -230,7 +230,8 @@ def test_conv_implicit_gemm_layer_matches_oracle(algo, Nb, C, O, H, W, k, stride
     dy = torch.randn_like(y)
     y.backward(dy)
     mod.restore()
-    assert _lib.launch_count() - before >= 5  # merge + fprop + (dgrad) + wgrad + factor grads
+    engine_dgrad = stride == 1 and O % 64 == 0
+    assert _lib.launch_count() - before >= (5 if engine_dgrad else 4)  # merge + fprop + (dgrad) + wgrad + factor grads
     p = {kk: v.detach() for kk, v in mod.named_parameters()}
     conv = dict(stride=base.stride, padding=base.padding, dilation=base.dilation, groups=1)
     oy, odx, og = O_.layer_forward_backward(oalgo, x.detach(), base.weight, base.bias, p, cfg, dy, conv, torch.bfloat16)

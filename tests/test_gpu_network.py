@@ -126,9 +126,9 @@ def test_mixed_algo_preset_runs_and_trains():
     kinds = {type(l).__name__ for l in net.loras}
     assert {"LoConModule", "LohaModule", "LokrModule"} <= kinds
     net.apply_to(None, unet, False, True)
-    opt = torch.optim.SGD(net.parameters(), lr=1e-2)
+    opt = torch.optim.Adam(net.parameters(), lr=5e-3)
     losses = []
-    for _ in range(6):
+    for _ in range(30):
         opt.zero_grad(set_to_none=True)
         with torch.autocast("cuda", dtype=torch.bfloat16):
             out = unet(st["sample"], st["timesteps"], st["context"])
@@ -138,7 +138,8 @@ def test_mixed_algo_preset_runs_and_trains():
         losses.append(float(loss))
     net.restore()
     assert all(torch.isfinite(torch.tensor(losses)))
-    assert losses[-1] < losses[0], losses
+    # the target is pure noise, so the attainable drop is small — but it must be a real, monotone-ish drop
+    assert min(losses[-5:]) < losses[0] - 1e-3, losses
 
 
 def test_cuda_graph_capture_of_a_step():

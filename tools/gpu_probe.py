@@ -220,6 +220,19 @@ CASES += [
     ("gemm", dict(M=32768, N=640, K=640, a_mn=False, b_mn=False, out="16", bias=True, force="pair128")),
     ("gemm", dict(M=8192, N=10240, K=1280, a_mn=False, b_mn=False, out="16", bias=True)),
     ("gemm", dict(M=8192, N=1280, K=1280, a_mn=False, b_mn=False, out="16", bias=True)),
+    # runtime BLOCK_N (multiples of 32) + TMA-store epilogue
+    ("gemm", dict(M=1000, N=328, K=200, a_mn=False, b_mn=False, out="16", bias=True, force="pair160")),
+    ("gemm", dict(M=1000, N=328, K=200, a_mn=False, b_mn=False, out="16", bias=True, force="single96")),
+    ("gemm", dict(M=300, N=72, K=136, a_mn=False, b_mn=False, out="16", bias=True, force="single32")),
+    ("gemm", dict(M=520, N=200, K=64, a_mn=False, b_mn=False, out="16", bias=False, force="pair64")),
+    ("gemm", dict(M=8192, N=1280, K=1280, a_mn=False, b_mn=False, out="16", bias=True, force="pair160")),
+    ("gemm", dict(M=8192, N=1280, K=1280, a_mn=False, b_mn=False, out="16", bias=True, force="pair224")),
+    ("gemm", dict(M=8192, N=1280, K=5120, a_mn=False, b_mn=False, out="16", bias=True)),
+    ("gemm", dict(M=32768, N=640, K=640, a_mn=False, b_mn=False, out="16", bias=True)),
+    ("gemm", dict(M=32768, N=5120, K=640, a_mn=False, b_mn=False, out="16", bias=True)),
+    ("gemm", dict(M=8192, N=1280, K=1280, a_mn=False, b_mn=True, out="16", bias=False)),
+    ("gemm", dict(M=1280, N=1280, K=8192, a_mn=True, b_mn=True, out="f32", bias=False, split_k=0)),
+    ("gemm", dict(M=616, N=1280, K=2048, a_mn=False, b_mn=False, out="16", bias=False)),
     ("weight", dict(algo="locon", N=1280, K=1280, r=16)),
     ("weight", dict(algo="locon", N=320, K=2880, r=8, fdt="bf16")),
     ("conv", dict(Nb=2, H=8, W=8, C=64, O=64, R=3, pad=1, stride=1)),
