@@ -39,7 +39,9 @@ enum {
   LYCO_ALGO_LOHA = 1,  /* lycoris/modules/loha.py   */
   LYCO_ALGO_LOKR = 2,  /* lycoris/modules/lokr.py   */
   LYCO_ALGO_IA3 = 3,   /* lycoris/modules/ia3.py    */
-  LYCO_ALGO_DYLORA = 4 /* lycoris/modules/dylora.py (uses the LOCON kernels) */
+  LYCO_ALGO_DYLORA = 4, /* lycoris/modules/dylora.py (uses the LOCON kernels) */
+  LYCO_ALGO_RAW = 5     /* rank-r products already formed by lyco_gemm (K = r): f0 = raw1, f1 = raw2 or NULL,
+                           16-bit [N, K'] arrays in f_dtype; merge only (tensor-core path of LOCON/DYLORA/LOHA) */
 };
 
 /* ------------------------------------------------------------------------- */
@@ -180,6 +182,13 @@ int lyco_merge_weight(const lyco_delta_desc_t* d, const void* W, void* W_out,
  */
 int lyco_factor_grads(const lyco_delta_desc_t* d, const float* dW, const void* W,
                       float* g0, float* g1, float* g2, float* g3, void* stream);
+
+/*
+ * G[i] = rnd16(gscale * dW[i] * (P ? P[i] : 1)) for i < n (n % 8 == 0): the 16-bit operand of the skinny
+ * gradient contractions on the tensor-core path (g_up = G·downᵀ, g_down = upᵀ·G; LoHa: P = the other
+ * Hadamard factor, recomputed — lycoris/functional/loha.py:18-30).
+ */
+int lyco_grad_prep(const float* dW, const void* P, void* G, int64_t n, float gscale, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -316,6 +316,11 @@ int check_desc(const lyco_delta_desc_t* d) {
         return fail("lokr factor shapes (%d,%d)x(%d,%d) do not tile %d x %d", d->up, d->uq, d->vp, d->vq,
                     d->out_dim, d->in_dim);
       break;
+    case LYCO_ALGO_RAW:
+      if (!d->f0) return fail("raw merge needs f0");
+      if (d->f_dtype != LYCO_BF16 && d->f_dtype != LYCO_F16) return fail("raw products must be 16-bit");
+      if ((static_cast<int64_t>(d->out_dim) * d->in_dim) % 8) return fail("raw merge needs N*K' %% 8 == 0");
+      break;
     case LYCO_ALGO_IA3:
       if (!d->f0) return fail("ia3 needs f0");
       if (d->on_input && (d->ia3_group <= 0 || d->in_dim % d->ia3_group))
@@ -547,6 +552,15 @@ int lyco_merge_weight(const lyco_delta_desc_t* d, const void* W, void* W_out, vo
       lyco::merge_ia3_kernel<<<grid, 256, 0, stream>>>(*d, w, wo);
       break;
     }
+    case LYCO_ALGO_RAW: {
+      if (!aligned16 || (reinterpret_cast<uintptr_t>(d->f0) & 15) || (d->f1 && (reinterpret_cast<uintptr_t>(d->f1) & 15)))
+        return fail("lyco_merge_weight(raw): arrays must be 16-byte aligned");
+      int grid = static_cast<int>((total / 8 + 255) / 256);
+      const int cap = di.sms * 16;
+      if (grid > cap) grid = cap;
+      lyco::merge_raw_kernel<<<grid, 256, 0, stream>>>(*d, w, wo);
+      break;
+    }
   }
   LYCO_CUDA(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -597,6 +611,8 @@ int lyco_factor_grads(const lyco_delta_desc_t* d, const float* dW, const void* W
       }
       break;
     }
+    case LYCO_ALGO_RAW:
+      return fail("lyco_factor_grads: LYCO_ALGO_RAW has no factor gradients (use lyco_grad_prep + lyco_gemm)");
     case LYCO_ALGO_IA3: {
       if (!g0 || !W) return fail("lyco_factor_grads: ia3 needs g0 and W");
       const uint16_t* w = static_cast<const uint16_t*>(W);
@@ -610,6 +626,24 @@ int lyco_factor_grads(const lyco_delta_desc_t* d, const float* dW, const void* W
       break;
     }
   }
+  LYCO_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+int lyco_grad_prep(const float* dW, const void* P, void* G, int64_t n, float gscale, int dtype, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!dW || !G || n <= 0 || (n % 8)) return fail("lyco_grad_prep: need dW, G and n %% 8 == 0");
+  if (dtype != LYCO_BF16 && dtype != LYCO_F16) return fail("lyco_grad_prep: output dtype must be 16-bit");
+  if ((reinterpret_cast<uintptr_t>(dW) | reinterpret_cast<uintptr_t>(G) | reinterpret_cast<uintptr_t>(P)) & 15)
+    return fail("lyco_grad_prep: arrays must be 16-byte aligned");
+  DeviceInfo di;
+  if (device_info(&di)) return 1;
+  int grid = static_cast<int>((n / 8 + 255) / 256);
+  const int cap = di.sms * 16;
+  if (grid > cap) grid = cap;
+  lyco::grad_prep_kernel<<<grid, 256, 0, stream>>>(dW, static_cast<const uint16_t*>(P), static_cast<uint16_t*>(G), n / 8,
+                                                   gscale, dtype);
   LYCO_CUDA(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;

@@ -209,6 +209,59 @@ __global__ void __launch_bounds__(256) merge_lokr_kernel(lyco_delta_desc_t d, co
   }
 }
 
+// RAW: the rank-r products were formed on the tensor cores (lyco_gemm with K = r) and arrive as 16-bit
+// [N, K'] arrays: W' = rnd(W + chain(raw1 [* raw2])).  Used for LoCon / DyLoRA (one product) and LoHa (two).
+__global__ void __launch_bounds__(256) merge_raw_kernel(lyco_delta_desc_t d, const uint16_t* __restrict__ W,
+                                                        uint16_t* __restrict__ Wout) {
+  const int64_t total8 = static_cast<int64_t>(d.out_dim) * d.in_dim / 8;
+  const Chain ch{d.pre_round, d.pre_dtype, d.w_dtype, d.m_pre, d.m_post1, d.m_post2};
+  const int pd = d.f_dtype;  // dtype of the raw products
+  const uint4* r1 = reinterpret_cast<const uint4*>(d.f0);
+  const uint4* r2 = reinterpret_cast<const uint4*>(d.f1);
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total8;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const uint4 wv = __ldg(reinterpret_cast<const uint4*>(W) + i);
+    const uint4 av = __ldg(r1 + i);
+    uint4 bv = make_uint4(0, 0, 0, 0);
+    if (r2) bv = __ldg(r2 + i);
+    const uint16_t* wh = reinterpret_cast<const uint16_t*>(&wv);
+    const uint16_t* ah = reinterpret_cast<const uint16_t*>(&av);
+    const uint16_t* bh = reinterpret_cast<const uint16_t*>(&bv);
+    uint4 ov;
+    uint16_t* oh = reinterpret_cast<uint16_t*>(&ov);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float raw = cvt16(ah[j], pd);
+      if (r2) raw *= cvt16(bh[j], pd);
+      oh[j] = to16(merged(cvt16(wh[j], d.w_dtype), apply_chain(raw, ch), d.w_dtype), d.w_dtype);
+    }
+    reinterpret_cast<uint4*>(Wout)[i] = ov;
+  }
+}
+
+// G = rnd16(gscale * dW [* P]) — operand of the skinny tensor-core gradient contractions
+__global__ void __launch_bounds__(256) grad_prep_kernel(const float* __restrict__ dW, const uint16_t* __restrict__ P,
+                                                        uint16_t* __restrict__ G, int64_t n8, float gscale, int dtype) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(dW) + 2 * i);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(dW) + 2 * i + 1);
+    float g[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint4 pv = make_uint4(0, 0, 0, 0);
+    if (P) pv = __ldg(reinterpret_cast<const uint4*>(P) + i);
+    const uint16_t* ph = reinterpret_cast<const uint16_t*>(&pv);
+    uint4 ov;
+    uint16_t* oh = reinterpret_cast<uint16_t*>(&ov);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = g[j] * gscale;
+      if (P) v *= cvt16(ph[j], dtype);
+      oh[j] = to16(v, dtype);
+    }
+    reinterpret_cast<uint4*>(G)[i] = ov;
+  }
+}
+
 // (IA)^3: W' = W * (1 + w*mult) on output rows or input channels (ia3.py:91-102)
 __global__ void __launch_bounds__(256) merge_ia3_kernel(lyco_delta_desc_t d, const uint16_t* __restrict__ W,
                                                         uint16_t* __restrict__ Wout) {

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "_lyco_b200.so")
 
 BF16, F16, F32 = 0, 1, 2
-ALGO_LOCON, ALGO_LOHA, ALGO_LOKR, ALGO_IA3, ALGO_DYLORA = 0, 1, 2, 3, 4
+ALGO_LOCON, ALGO_LOHA, ALGO_LOKR, ALGO_IA3, ALGO_DYLORA, ALGO_RAW = 0, 1, 2, 3, 4, 5
 
 # every symbol include/lyco_b200.h declares (checked by the CPU test-suite)
 EXPORTED_SYMBOLS = (
@@ -28,6 +28,7 @@ EXPORTED_SYMBOLS = (
     "lyco_conv2d_wgrad",
     "lyco_merge_weight",
     "lyco_factor_grads",
+    "lyco_grad_prep",
 )
 
 
@@ -103,6 +104,8 @@ def _bind(lib):
     lib.lyco_factor_grads.argtypes = [
         POINTER(DeltaDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
     ]
+    lib.lyco_grad_prep.restype = c_int
+    lib.lyco_grad_prep.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_int, c_void_p]
     return lib
 
 

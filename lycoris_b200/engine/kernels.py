@@ -9,7 +9,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import ALGO_DYLORA, ALGO_IA3, ALGO_LOCON, ALGO_LOHA, ALGO_LOKR, BF16, F16, F32, DeltaDesc
+from ._lib import ALGO_DYLORA, ALGO_IA3, ALGO_LOCON, ALGO_LOHA, ALGO_LOKR, ALGO_RAW, BF16, F16, F32, DeltaDesc
 
 _DT = {torch.bfloat16: BF16, torch.float16: F16, torch.float32: F32}
 
@@ -99,10 +99,10 @@ def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, out_dtype=None, split_k=0, 
     return out
 
 
-def conv2d_supported(x, weight_shape, stride, padding, dilation, groups) -> bool:
+def conv2d_supported(x, weight_shape, stride, padding, dilation, groups, dtype=None) -> bool:
     """Geometry the implicit-GEMM kernels cover: 2-D, dilation 1, groups 1, C % 64 == 0, O % 8 == 0.
     (Activations must be NHWC; callers convert NCHW tensors with one transpose pass.)"""
-    if x.dim() != 4 or len(weight_shape) != 4 or x.dtype not in (torch.bfloat16, torch.float16):
+    if x.dim() != 4 or len(weight_shape) != 4 or (dtype or x.dtype) not in (torch.bfloat16, torch.float16):
         return False
     O, C, R, S = weight_shape
     if groups != 1 or tuple(dilation) != (1, 1) or stride[0] != stride[1] or not (1 <= stride[0] <= 8):
@@ -196,7 +196,17 @@ def factor_grads(desc: DeltaDesc, dW: torch.Tensor, W, shapes):
     return gs
 
 
+def grad_prep(dW: torch.Tensor, P, gscale: float, dtype: torch.dtype) -> torch.Tensor:
+    """``G = dtype(gscale * dW * (P or 1))`` — 16-bit operand for the skinny gradient contractions."""
+    _require_cuda(dW, P)
+    assert dW.dtype == torch.float32 and dW.is_contiguous()
+    G = torch.empty(dW.shape, device=dW.device, dtype=dtype)
+    rc = _lib.load().lyco_grad_prep(_ptr(dW), _ptr(P), _ptr(G), dW.numel(), float(gscale), dtype_code(dtype), _stream())
+    _lib.check(rc, "grad_prep")
+    return G
+
+
 __all__ = [
     "gemm", "gemm_supported", "conv2d_supported", "as_nhwc", "conv2d_fprop", "conv2d_wgrad", "make_desc", "merge_weight", "factor_grads", "dtype_code",
-    "ALGO_LOCON", "ALGO_LOHA", "ALGO_LOKR", "ALGO_IA3", "ALGO_DYLORA", "BF16", "F16", "F32",
+    "grad_prep", "ALGO_LOCON", "ALGO_LOHA", "ALGO_LOKR", "ALGO_IA3", "ALGO_DYLORA", "ALGO_RAW", "BF16", "F16", "F32",
 ]

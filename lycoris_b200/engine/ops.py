@@ -102,9 +102,9 @@ def _dense_tn_f32(a, b):
 _CONV_ENGINE = os.environ.get("LYCO_CONV_IMPL", "engine") != "cudnn"
 
 
-def _conv_engine_ok(x, w, cp):
+def _conv_engine_ok(x, w, cp, dtype=None):
     return (_CONV_ENGINE and w.dim() == 4 and not isinstance(cp["padding"], str)
-            and K.conv2d_supported(x, w.shape, cp["stride"], cp["padding"], cp["dilation"], cp["groups"]))
+            and K.conv2d_supported(x, w.shape, cp["stride"], cp["padding"], cp["dilation"], cp["groups"], dtype))
 
 
 def _conv_forward(x, w, bias, cp):
@@ -148,6 +148,63 @@ def _is_pointwise(cp, w):
             and tuple(cp["padding"]) == (0, 0) and cp["groups"] == 1)
 
 
+# ------------------------------------------------------- low-rank products on the tensor cores
+# LoCon / DyLoRA / LoHa: when the factor product is a 16-bit matmul in the reference (bf16/fp16 adapters or
+# autocast) and r % 8 == 0, the rank-r products and their gradients run on the tcgen05 GEMM (K = r, or
+# N = r) instead of the CUDA-core tile kernels; LYCO_LOWRANK=simt forces the latter.
+_LOWRANK_TC = os.environ.get("LYCO_LOWRANK", "tc") != "simt"
+_LOWRANK_ALGOS = (K.ALGO_LOCON, K.ALGO_DYLORA, K.ALGO_LOHA)
+
+
+def _lowrank_tc_dtype(spec, factors, out_dim, in_dim, ac_dtype):
+    """dtype of the tensor-core product path, or None when the layer has to use the SIMT kernels."""
+    if not _LOWRANK_TC or spec.algo not in _LOWRANK_ALGOS:
+        return None
+    prod = ac_dtype if ac_dtype is not None else factors[0].dtype
+    if prod not in _HALF or spec.rank % 8 or out_dim % 8 or in_dim % 8:
+        return None
+    return prod
+
+
+def _lowrank_operands(spec, factors, prod):
+    """16-bit copies of the factors as the matmul sees them (DyLoRA folds alpha/(b+1)*mult into `down`
+    in the parameter dtype first, dylora.py:117)."""
+    ops = [f.to(prod) for f in factors]
+    if spec.algo == K.ALGO_DYLORA and spec.m_in != 1.0:
+        ops[1] = (factors[1] * spec.m_in).to(prod)
+    return [o.contiguous() for o in ops]
+
+
+def _lowrank_merge(spec, factors, W, prod, out_dim, in_dim):
+    f = _lowrank_operands(spec, factors, prod)
+    raws = [K.gemm(f[0], f[1], b_mn=True)]  # [N, r] x [r, K'] -> [N, K'], rounded to `prod` like the reference's matmul
+    if spec.algo == K.ALGO_LOHA:
+        raws.append(K.gemm(f[2], f[3], b_mn=True))
+    desc = K.make_desc(K.ALGO_RAW, out_dim, in_dim, factors=raws, w_dtype=W.dtype, pre_round=1, pre_dtype=prod,
+                       m_pre=spec.m_pre, m_post1=spec.m_post1, m_post2=spec.m_post2)
+    return K.merge_weight(desc, W)
+
+
+def _lowrank_grads(spec, factors, dWm, prod):
+    """Factor gradients from fp32 dW' with skinny tensor-core contractions (fp32 outputs)."""
+    f = _lowrank_operands(spec, factors, prod)
+    gscale = spec.m_pre * spec.m_post1 * spec.m_post2
+    f32 = torch.float32
+    if spec.algo != K.ALGO_LOHA:
+        G = K.grad_prep(dWm, None, gscale, prod)
+        g_up = K.gemm(G, f[1], out_dtype=f32)                          # G · downᵀ          [N, r]
+        g_down = K.gemm(f[0], G, a_mn=True, b_mn=True, out_dtype=f32)  # upᵀ · G            [r, K']
+        if spec.algo == K.ALGO_DYLORA and spec.m_in != 1.0:
+            g_down = g_down * spec.m_in
+        return [g_up, g_down]
+    P1 = K.gemm(f[0], f[1], b_mn=True)  # recomputed, never cached (functional/loha.py:18-30)
+    P2 = K.gemm(f[2], f[3], b_mn=True)
+    G1 = K.grad_prep(dWm, P2, gscale, prod)
+    G2 = K.grad_prep(dWm, P1, gscale, prod)
+    return [K.gemm(G1, f[1], out_dtype=f32), K.gemm(f[0], G1, a_mn=True, b_mn=True, out_dtype=f32),
+            K.gemm(G2, f[3], out_dtype=f32), K.gemm(f[2], G2, a_mn=True, b_mn=True, out_dtype=f32)]
+
+
 # ------------------------------------------------------------------ autograd nodes
 class _AdapterContraction(torch.autograd.Function):
     """y = op(x, merge(W, factors), bias) with everything on the sm_100a kernels."""
@@ -157,8 +214,12 @@ class _AdapterContraction(torch.autograd.Function):
         factors_u = _uniform_factors(factors)
         out_dim = W.shape[0]
         in_dim = W.numel() // out_dim
-        desc = _build_desc(spec, factors_u, W.dtype, ac_dtype, out_dim, in_dim)
-        Wm = K.merge_weight(desc, W)
+        prod = _lowrank_tc_dtype(spec, factors_u, out_dim, in_dim, ac_dtype)
+        if prod is not None:
+            Wm = _lowrank_merge(spec, factors_u, W, prod, out_dim, in_dim)
+        else:
+            desc = _build_desc(spec, factors_u, W.dtype, ac_dtype, out_dim, in_dim)
+            Wm = K.merge_weight(desc, W)
         if delta_only:
             Wm = Wm - W  # exact on W's grid: this is the reference's `new_weight - base_weight`
         if conv is None:
@@ -203,8 +264,12 @@ class _AdapterContraction(torch.autograd.Function):
         grads = [None] * len(factors)
         if need_f:
             factors_u = _uniform_factors(factors)
-            desc = _build_desc(spec, factors_u, W.dtype, ctx.ac_dtype, out_dim, in_dim)
-            gs = K.factor_grads(desc, dWm.contiguous(), W, [f.shape for f in factors_u])
+            prod = _lowrank_tc_dtype(spec, factors_u, out_dim, in_dim, ctx.ac_dtype)
+            if prod is not None:
+                gs = _lowrank_grads(spec, factors_u, dWm.contiguous(), prod)
+            else:
+                desc = _build_desc(spec, factors_u, W.dtype, ctx.ac_dtype, out_dim, in_dim)
+                gs = K.factor_grads(desc, dWm.contiguous(), W, [f.shape for f in factors_u])
             for i, (g, f) in enumerate(zip(gs, factors)):
                 if ctx.needs_input_grad[7 + i]:
                     grads[i] = g.to(f.dtype) if g.dtype != f.dtype else g
@@ -287,10 +352,6 @@ def adapter_forward(module, x, args, kwargs, native_spec, assemble_fallback):
         W = W.to(cdt)
     if bias is not None and bias.dtype != cdt:
         bias = bias.to(cdt)
-    if x.dtype != cdt:
-        if ac is None:
-            raise RuntimeError(f"lycoris_b200: input dtype {x.dtype} != weight dtype {cdt} (no autocast active)")
-        x = x.to(cdt)
     if not W.is_contiguous():
         W = W.contiguous()
 
@@ -298,6 +359,14 @@ def adapter_forward(module, x, args, kwargs, native_spec, assemble_fallback):
     conv = _conv_params(module) if is_conv else None
     if is_conv and isinstance(conv["padding"], str):
         raise NotImplementedError("lycoris_b200: string padding modes are not supported")
+    if x.dtype != cdt:
+        if ac is None:
+            raise RuntimeError(f"lycoris_b200: input dtype {x.dtype} != weight dtype {cdt} (no autocast active)")
+        if is_conv and x.dim() == 4 and _conv_engine_ok(x, W, conv, cdt):
+            # autocast cast fused with the NCHW -> NHWC transpose the im2col producer needs (one pass, not two)
+            x = x.to(cdt, memory_format=torch.channels_last)
+        else:
+            x = x.to(cdt)
     if is_conv and _is_pointwise(conv, W) and x.is_contiguous(memory_format=torch.channels_last) and x.dim() == 4:
         # NHWC 1x1 convolution is a plain linear over channels: run it on the tcgen05 GEMM
         y = adapter_forward_pointwise(module, x, W, bias, ac, native_spec, assemble_fallback, args, kwargs)

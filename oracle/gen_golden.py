@@ -240,6 +240,41 @@ def main():
         torch.save(cases, os.path.join(OUT, f"layers_{regime}.pt"))
     print(f"{n} layer cases: oracle == reference (bit-exact), fixtures written")
 
+    # 2b. BASELINE.json configs[0]: LoCon dim 4 alpha 1 on nn.Linear(768, 768) through the generic wrapper,
+    #     fp32, X ~ N(0,1) [8,77,768], loss = y.float().pow(2).mean()   
+    torch.manual_seed(0)
+    net_base = nn.Sequential(nn.Linear(768, 768))
+    lycoris.wrapper.LycorisNetwork.apply_preset(
+        {"target_module": ["Linear"], "target_name": [], "module_algo_map": {}, "name_algo_map": {},
+         "exclude_name": [], "use_fnmatch": False, "lora_prefix": "lycoris", "enable_conv": True})
+    torch.manual_seed(1)
+    net = lycoris.create_lycoris(net_base, 1.0, linear_dim=4, linear_alpha=1, algo="locon")
+    net.apply_to()
+    perturb(net, 11)
+    for p_ in net_base.parameters():
+        p_.requires_grad_(False)
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(8, 77, 768, generator=g)
+    y = net_base(x)
+    loss = y.float().pow(2).mean()
+    loss.backward()
+    lora = net.loras[0]
+    # inputs are re-generated from their seeds by the tests (checksums stored); only sample 0 of y is kept
+    cfg1 = {
+        "weight_sum": float(net_base[0].weight.double().sum()), "x_sum": float(x.double().sum()),
+        "bias": net_base[0].bias.detach().clone(),
+        "y0": y[0].detach().clone(), "loss": loss.detach().clone(), "lora_name": lora.lora_name,
+        "params": {k: v.detach().clone() for k, v in lora.named_parameters()},
+        "grads": {k: v.grad.clone() for k, v in lora.named_parameters()},
+        "scale": float(lora.scale),
+    }
+    net.restore()
+    yo = O.layer_forward("locon", x, net_base[0].weight.detach(), cfg1["bias"],
+                         {k: v for k, v in cfg1["params"].items()}, {"scale": cfg1["scale"], "multiplier": 1.0})
+    assert torch.equal(yo, y.detach())
+    torch.save(cfg1, os.path.join(OUT, "cfg1_locon_linear768.pt"))
+    print("cfg1 fixture written:", cfg1["lora_name"], float(cfg1["loss"]))
+
     # 3. structure
     with open(os.path.join(OUT, "structure.json"), "w") as fh:
         json.dump(structure_fixture(), fh)

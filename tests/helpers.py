@@ -136,3 +136,18 @@ def oracle_patch_network(net):
             org.forward = saved
 
     return restore
+
+
+def load_cfg1():
+    """BASELINE.json configs[0] fixture; weight / x are re-created from their seeds and checked against
+    the stored checksums (the fixture keeps only what cannot be regenerated: reference outputs)."""
+    c = torch.load(os.path.join(GOLDEN, "cfg1_locon_linear768.pt"), weights_only=False)
+    torch.manual_seed(0)
+    lin = nn.Linear(768, 768)
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(8, 77, 768, generator=g)
+    assert abs(float(lin.weight.double().sum()) - c["weight_sum"]) < 1e-9, "seeded weight differs from the fixture's"
+    assert abs(float(x.double().sum()) - c["x_sum"]) < 1e-9, "seeded input differs from the fixture's"
+    assert torch.equal(lin.bias.detach(), c["bias"])
+    c["weight"], c["x"] = lin.weight.detach().clone(), x
+    return c

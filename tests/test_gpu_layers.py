@@ -239,3 +239,112 @@ def test_conv_implicit_gemm_layer_matches_oracle(algo, Nb, C, O, H, W, k, stride
     assert float((x.grad.float() - odx.float()).abs().max()) <= Y_REL * float(odx.float().abs().max())
     for kk, g in og.items():
         assert rel_err(getattr(mod, kk.split(".")[0]).weight.grad if "." in kk else getattr(mod, kk).grad, g) <= G_REL, kk
+
+
+LOWRANK_TC_CASES = [
+    ("locon", 16, "autocast"), ("locon", 16, "bf16"), ("locon", 64, "autocast"),
+    ("loha", 32, "autocast"), ("loha", 8, "bf16"), ("dylora", 16, "autocast"),
+]
+
+
+@pytest.mark.parametrize("algo,r,regime", LOWRANK_TC_CASES)
+def test_lowrank_tensor_core_path_matches_oracle(algo, r, regime):
+    """r % 8 == 0 and a 16-bit product domain: the rank-r products and their gradients run as K = r / N = r
+    contractions on the tcgen05 GEMM (RAW merge + grad_prep); compared with the oracle on device."""
+    import torch.nn as nn
+
+    import lycoris_b200 as L
+    from lycoris_b200.engine import ops
+    from oracle import lyco_oracle as O_
+
+    assert ops._LOWRANK_TC
+    torch.manual_seed(r)
+    base = nn.Linear(640, 1280).cuda().to(torch.bfloat16)
+    for p in base.parameters():
+        p.requires_grad_(False)
+    if algo == "locon":
+        mod = L.LoConModule("t", base, 1.0, r, r / 2).cuda()
+        with torch.no_grad():
+            mod.lora_up.weight.normal_(0, 0.05)
+        cfg = {"scale": mod.scale, "multiplier": 1.0}
+        params = lambda: {"lora_up.weight": mod.lora_up.weight, "lora_down.weight": mod.lora_down.weight}  # noqa: E731
+    elif algo == "loha":
+        mod = L.LohaModule("t", base, 1.0, r, r / 2).cuda()
+        with torch.no_grad():
+            mod.hada_w2_a.normal_(0, 0.1)
+        cfg = {"scale": mod.scale, "multiplier": 1.0}
+        params = lambda: {k: getattr(mod, k) for k in ("hada_w1_a", "hada_w1_b", "hada_w2_a", "hada_w2_b")}  # noqa: E731
+    else:
+        mod = L.DyLoraModule("t", base, 1.0, r, r / 2, block_size=8).cuda()
+        with torch.no_grad():
+            for u in mod.up_list:
+                u.normal_(0, 0.05)
+        cfg = {"alpha": mod.alpha, "multiplier": 1.0, "scale": 1.0}
+        params = lambda: {"up_list": list(mod.up_list), "down_list": list(mod.down_list)}  # noqa: E731
+    ac = None
+    if regime == "bf16":
+        mod.to(torch.bfloat16)
+    else:
+        ac = torch.bfloat16
+    x = torch.randn(4, 77, 640, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    dy = torch.randn(4, 77, 1280, device="cuda", dtype=torch.bfloat16)
+    mod.apply_to()
+    random.seed(5)
+    if ac is not None:
+        with torch.autocast("cuda", dtype=ac):
+            y = base(x)
+    else:
+        y = base(x)
+    y.backward(dy)
+    mod.restore()
+    if algo == "dylora":
+        random.seed(5)
+        cfg["b"] = O_.draw_dylora_block(mod.block_count)
+    oy, odx, og = O_.layer_forward_backward("dylora" if algo == "dylora" else algo, x.detach(), base.weight,
+                                            base.bias, {k: (v if isinstance(v, list) else v.detach()) for k, v in params().items()},
+                                            cfg, dy, None, ac)
+    assert float((y.detach().float() - oy.float()).abs().max()) <= Y_REL * float(oy.float().abs().max())
+    assert float((x.grad.float() - odx.float()).abs().max()) <= Y_REL * float(odx.float().abs().max())
+    for k, g in og.items():
+        if isinstance(g, list):
+            mine = [p.grad for p in getattr(mod, k)]
+            for a, b in zip(mine, g):
+                assert (a is None) == (b is None), k
+                if b is not None:
+                    assert rel_err(a, b) <= G_REL, k
+        else:
+            tgt = mod.lora_up.weight if k == "lora_up.weight" else mod.lora_down.weight if k == "lora_down.weight" else getattr(mod, k)
+            assert rel_err(tgt.grad, g) <= G_REL, (k, rel_err(tgt.grad, g))
+
+
+def test_cfg1_locon_linear768_on_gpu_under_autocast():
+    """configs[0] through the generic wrapper on the GPU: fp32 base + fp32 adapter under autocast(bf16)
+    against the reference's fp32 CPU result, at bf16 tolerance (the engine has no fp32-operand GEMM)."""
+    import torch.nn as nn
+
+    from helpers import load_cfg1
+    from lycoris_b200.wrapper import LycorisNetwork, create_lycoris
+
+    c = load_cfg1()
+    base = nn.Sequential(nn.Linear(768, 768))
+    base[0].weight.data = c["weight"].clone()
+    base[0].bias.data = c["bias"].clone()
+    base.cuda().requires_grad_(False)
+    LycorisNetwork.apply_preset({"target_module": ["Linear"], "target_name": []})
+    net = create_lycoris(base, 1.0, linear_dim=4, linear_alpha=1, algo="locon")
+    net.apply_to()
+    net.cuda()
+    with torch.no_grad():
+        for k, v in net.loras[0].named_parameters():
+            v.copy_(c["params"][k])
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = base(c["x"].cuda())
+    loss = y.float().pow(2).mean()
+    loss.backward()
+    net.restore()
+    ref_y = c["y0"]
+    assert float((y[0].detach().float().cpu() - ref_y).abs().max()) <= 2.0 ** -6 * float(ref_y.abs().max())
+    assert abs(float(loss) - float(c["loss"])) <= 1e-2 * abs(float(c["loss"]))
+    for k, g in c["grads"].items():
+        mine = dict(net.loras[0].named_parameters())[k].grad.cpu()
+        assert rel_err(mine, g) <= 5e-2, (k, rel_err(mine, g))
