@@ -109,6 +109,9 @@ def network_args(algo):
     raise KeyError(algo)
 
 
+ALGO_NOTE = {"lokr": "factor 8, full-dim", "locon": "dim 16 conv_dim 8 alpha 8", "loha": "dim 32 conv_dim 16"}
+
+
 def perturb_zero_factors(net, seed=1):
     import torch
 
@@ -328,7 +331,7 @@ def run_engine(args):
         return
     steps_per_s = world * 1000.0 / ms_step
     result = {
-        "metric": "SDXL-UNet+LoKr fwd+bwd steps/sec",
+        "metric": f"SDXL-UNet+{ {'lokr': 'LoKr', 'locon': 'LoCon', 'loha': 'LoHa'}[args.algo] } fwd+bwd steps/sec",
         "value": steps_per_s,
         "unit": "steps/s",
         "n_gpus": world,
@@ -342,7 +345,7 @@ def run_engine(args):
         "data": "synthetic",
         "impl": "engine",
         "config": {
-            "workload": f"{cfg.name}-unet-skeleton + {args.algo} (factor 8, full-dim) via lycoris_b200.kohya, preset full, "
+            "workload": f"{cfg.name}-unet-skeleton + {args.algo} ({ALGO_NOTE[args.algo]}) via lycoris_b200.kohya, preset full, "
                         f"per-GPU batch {args.batch}, latents {args.sample_size or cfg.sample_size}^2, fwd+bwd, "
                         "bf16 base / fp32 adapter / autocast",
             "wrapped_layers": n_layers,

@@ -27,6 +27,18 @@ def main():
             dw = k.gemm(dY, X, a_mn=True, b_mn=True, out_dtype=torch.float32)
             g = k.factor_grads(d, dw, None, [w1.shape, w2.shape])
         torch.cuda.synchronize()
+    # 3x3 convolution, SDXL 1280-channel block at 32x32 (batch 8): fprop, dgrad (fprop on dY), wgrad
+    Nb, C, O, H = 8, 1280, 1280, 32
+    x = torch.randn(Nb, C, H, H, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    dy = torch.randn(Nb, O, H, H, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(O, C, 3, 3, device="cuda") * 0.01).to(torch.bfloat16)
+    wk = w.permute(0, 2, 3, 1).reshape(O, 9 * C)
+    wd = w.flip(2, 3).permute(1, 2, 3, 0).reshape(C, 9 * O)
+    for _ in range(reps):
+        k.conv2d_fprop(x, wk, None, 3, 3, (1, 1), 1)
+        k.conv2d_fprop(dy, wd, None, 3, 3, (1, 1), 1)
+        k.conv2d_wgrad(x, dy, 3, 3, (1, 1), 1)
+    torch.cuda.synchronize()
     print("ncu target done")
 
 
