@@ -109,6 +109,8 @@ def network_args(algo):
     raise KeyError(algo)
 
 
+NCU_TRAFFIC_DOMINANT = 183.3e6  # bytes per launch (52.8 MB read + 130.5 MB written), see profiles/
+
 ALGO_NOTE = {"lokr": "factor 8, full-dim", "locon": "dim 16 conv_dim 8 alpha 8", "loha": "dim 32 conv_dim 16"}
 
 
@@ -285,6 +287,17 @@ def run_engine(args):
     K.set_gemm_profiler(None)
     gemm_ms = sum(e0.elapsed_time(e1) for e0, e1, *_ in sink)
     gemm_flops = sum(f for _, _, f, *_ in sink)
+    if args.kernel_table and rank == 0:
+        by_shape = {}
+        for e0_, e1_, fl, M_, N_, K_ in sink:
+            a = by_shape.setdefault((M_, N_, K_), [0, 0.0, 0.0])
+            a[0] += 1
+            a[1] += e0_.elapsed_time(e1_)
+            a[2] += fl
+        with open(args.kernel_table + ".gemm_shapes", "w") as fh:
+            fh.write("lyco_gemm calls of one eager step by (M, N, K): count, total ms (event-bracketed), TFLOP/s\n")
+            for (M_, N_, K_), (cnt, ms_, fl) in sorted(by_shape.items(), key=lambda kv: -kv[1][1]):
+                fh.write(f"{ms_:9.3f} ms {cnt:5d}  M={M_:7d} N={N_:6d} K={K_:7d}  {fl / ms_ / 1e9:8.1f} TF\n")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     step()
@@ -311,11 +324,13 @@ def run_engine(args):
             for name, (cnt, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
                 fh.write(f"{t / 1e3:10.3f} ms {100 * t / tot:5.1f}% {cnt:6d}  {name}\n")
     if args.nvtx_step:
+        # start/end (not push/pop) ranges are process-wide: backward kernels are launched from autograd's
+        # worker thread and would fall outside a thread-local push/pop range
         torch.cuda.synchronize()
-        torch.cuda.nvtx.range_push("lyco_step")
+        rid = torch.cuda.nvtx.range_start("lyco_step")
         step()
         torch.cuda.synchronize()
-        torch.cuda.nvtx.range_pop()
+        torch.cuda.nvtx.range_end(rid)
 
     peaks = {}
     try:
@@ -366,7 +381,10 @@ def run_engine(args):
             "bound": "tensor", "kernel": "gemm_sm100_kernel (fwd / dgrad / wgrad of the wrapped Linear layers)",
             "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1400",
-            "traffic": None,
+            # dram__bytes_read+write per launch of the step's dominant GEMM (GEGLU proj forward, M=8192 N=10240
+            # K=1280) from the committed `ncu --set full` capture profiles/r01_ncu_full_summary.txt
+            "traffic": NCU_TRAFFIC_DOMINANT if args.model == "sdxl" else None,
+            "traffic_shape": "M=8192 N=10240 K=1280 fwd: algorithmic 2*(MK+NK+MN) = 215.0e6 B" if args.model == "sdxl" else None,
             "gemm_launches_per_step": len(sink), "gemm_ms_per_step": gemm_ms, "gemm_share_of_eager_step": gemm_ms / eager_ms,
             "algorithmic_tflop_per_step": gemm_flops / 1e12,
         },
