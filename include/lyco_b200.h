@@ -74,6 +74,8 @@ uint64_t lyco_launch_count(void);
  *   ab_dtype: LYCO_BF16 or LYCO_F16.
  *   bias / bias_dtype: optional [N] vector added in the epilogue (NULL = none).
  *   split_k: 0 = choose automatically; otherwise number of reduction splits.
+ *   accumulate: fp32 C only — C += A·Bᵀ (fp32 atomics, no zero fill).  Lets fp32 layers be contracted
+ *            as three bf16 products (hi·hi + hi·lo + lo·hi) into one fp32 accumulator.
  *
  * Replaces, per wrapped layer and step, the ATen library calls at
  *   forward   base + delta contraction  lycoris/modules/locon.py:317,331
@@ -87,7 +89,7 @@ int lyco_gemm(const void* A, int a_mn_major, int64_t lda,
               void* C, int c_dtype, int64_t ldc,
               const void* bias, int bias_dtype,
               int M, int N, int K,
-              int ab_dtype, int split_k, void* stream);
+              int ab_dtype, int split_k, int accumulate, void* stream);
 
 /* ------------------------------------------------------------------------- */
 /* implicit-GEMM convolution (tcgen05 + TMA im2col)                           */

@@ -352,8 +352,9 @@ int lyco_device_check(int device) {
 
 int lyco_gemm(const void* A, int a_mn_major, int64_t lda, const void* B, int b_mn_major, int64_t ldb,
               void* C, int c_dtype, int64_t ldc, const void* bias, int bias_dtype, int M, int N, int K,
-              int ab_dtype, int split_k, void* stream_) {
+              int ab_dtype, int split_k, int accumulate, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (accumulate && c_dtype != LYCO_F32) return fail("lyco_gemm: accumulate needs an fp32 C");
   if (M <= 0 || N <= 0 || K <= 0) return fail("lyco_gemm: empty problem %d x %d x %d", M, N, K);
   if (!A || !B || !C) return fail("lyco_gemm: null operand");
   if (ab_dtype != LYCO_BF16 && ab_dtype != LYCO_F16) return fail("lyco_gemm: operands must be bf16/f16");
@@ -406,8 +407,8 @@ int lyco_gemm(const void* A, int a_mn_major, int64_t lda, const void* B, int b_m
 
   int epi = lyco::EPI_STORE16;
   if (c_dtype == LYCO_F32) {
-    epi = splits > 1 ? lyco::EPI_ATOMIC_F32 : lyco::EPI_STORE_F32;
-    if (splits > 1) {
+    epi = (splits > 1 || accumulate) ? lyco::EPI_ATOMIC_F32 : lyco::EPI_STORE_F32;
+    if (splits > 1 && !accumulate) {
       if (ldc == N) LYCO_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * static_cast<size_t>(M) * N, stream));
       else LYCO_CUDA(cudaMemset2DAsync(C, ldc * sizeof(float), 0, N * sizeof(float), M, stream));
     }

@@ -84,7 +84,7 @@ def _bind(lib):
         c_void_p, c_int, c_int64,  # C
         c_void_p, c_int,  # bias
         c_int, c_int, c_int,  # M N K
-        c_int, c_int, c_void_p,  # ab_dtype, split_k, stream
+        c_int, c_int, c_int, c_void_p,  # ab_dtype, split_k, accumulate, stream
     ]
     lib.lyco_conv2d_fprop.restype = c_int
     lib.lyco_conv2d_fprop.argtypes = [

@@ -57,7 +57,7 @@ def set_gemm_profiler(sink):
     _gemm_profile = sink
 
 
-def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, out_dtype=None, split_k=0, out=None):
+def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, out_dtype=None, split_k=0, out=None, accumulate=False):
     """``C[M,N] = A · Bᵀ (+ bias)``.
 
     ``a`` is stored ``[M, K]`` (``a_mn=False``) or ``[K, M]`` (``a_mn=True``); likewise ``b`` with
@@ -90,7 +90,7 @@ def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, out_dtype=None, split_k=0, 
         _ptr(b), int(b_mn), b.stride(0),
         _ptr(out), dtype_code(out.dtype), out.stride(0),
         _ptr(bias), dtype_code(bias.dtype) if bias is not None else 0,
-        M, N, K, dtype_code(a.dtype), int(split_k), _stream(),
+        M, N, K, dtype_code(a.dtype), int(split_k), int(bool(accumulate)), _stream(),
     )
     _lib.check(rc, "gemm")
     if prof is not None:

@@ -97,6 +97,55 @@ def _dense_tn_f32(a, b):
     return (a.t() @ b).float()
 
 
+# fp32 layers (no autocast): every operand is split x = hi + lo into two bf16 tensors and the contraction is
+# hi·hi + hi·lo + lo·hi accumulated in ONE fp32 C on the tcgen05 GEMM (the lo·lo term is below fp32 rounding of
+# the sum); relative error ~2^-16 per product instead of bf16's 2^-8.
+def _split_bf16(t):
+    hi = t.to(torch.bfloat16)
+    lo = (t - hi.float()).to(torch.bfloat16)
+    return hi, lo
+
+
+def _dense3(a, b, *, a_mn=False, b_mn=False, init=None):
+    """fp32 C = A·Bᵀ (+ init) from fp32 A, B as three bf16 products; shapes as in K.gemm."""
+    ah, al = _split_bf16(a)
+    bh, bl = _split_bf16(b)
+    M = a.shape[1] if a_mn else a.shape[0]
+    N = b.shape[1] if b_mn else b.shape[0]
+    out = torch.zeros((M, N), device=a.device, dtype=torch.float32) if init is None else init
+    for x, y in ((ah, bh), (ah, bl), (al, bh)):
+        K.gemm(x, y, a_mn=a_mn, b_mn=b_mn, out=out, out_dtype=torch.float32, accumulate=True)
+    return out
+
+
+def _f32_supported(*mats):
+    return all(t.dim() == 2 and t.is_contiguous() and t.shape[1] % 8 == 0 and t.dtype == torch.float32 for t in mats)
+
+
+class _MergedContractionF32(torch.autograd.Function):
+    """fp32 Linear on the engine: y = x·Wm^T + b with Wm assembled in fp32 by PyTorch ops."""
+
+    @staticmethod
+    def forward(ctx, x, Wm, bias):
+        x2 = x.reshape(-1, x.shape[-1]).contiguous()
+        Wc = Wm.contiguous()
+        init = None if bias is None else bias.float().expand(x2.shape[0], Wc.shape[0]).contiguous()
+        y = _dense3(x2, Wc, init=init).view(*x.shape[:-1], Wc.shape[0])
+        ctx.save_for_backward(x, Wm)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, Wm = ctx.saved_tensors
+        dy2 = dy.reshape(-1, Wm.shape[0]).float().contiguous()
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = _dense3(dy2, Wm.contiguous(), b_mn=True).view(x.shape)
+        if ctx.needs_input_grad[1]:
+            dw = _dense3(dy2, x.reshape(-1, x.shape[-1]).contiguous(), a_mn=True, b_mn=True)
+        return dx, dw, None
+
+
 # LYCO_CONV_IMPL=cudnn routes every k>1 convolution through aten/cuDNN (on the merged weight) instead of
 # the implicit-GEMM kernels; the default uses the engine whenever the layer is eligible (NHWC, C % 64 == 0).
 _CONV_ENGINE = os.environ.get("LYCO_CONV_IMPL", "engine") != "cudnn"
@@ -343,11 +392,10 @@ def adapter_forward(module, x, args, kwargs, native_spec, assemble_fallback):
     bias = None if org.bias is None else org.bias.detach()
     ac = _autocast_dtype()
     cdt = ac if ac is not None else W.dtype
+    if cdt == torch.float32:
+        return _adapter_forward_f32(module, x, args, kwargs, W, bias, assemble_fallback)
     if cdt not in _HALF:
-        raise NotImplementedError(
-            f"lycoris_b200: compute dtype {cdt} — the engine contracts bf16/fp16 operands "
-            "(fp32 accumulation); cast the base model to bf16/fp16 or run under torch.autocast"
-        )
+        raise NotImplementedError(f"lycoris_b200: compute dtype {cdt} is not supported (bf16 / fp16 / fp32)")
     if W.dtype != cdt:
         W = W.to(cdt)
     if bias is not None and bias.dtype != cdt:
@@ -387,6 +435,26 @@ def adapter_forward(module, x, args, kwargs, native_spec, assemble_fallback):
         if not plain:
             Wm = Wm - W
         y = _MergedContraction.apply(x, Wm, None if not plain else bias, conv)
+    return y if plain else base + y
+
+
+def _adapter_forward_f32(module, x, args, kwargs, W, bias, assemble_fallback):
+    """fp32 base + fp32 adapter without autocast (the reference's CPU-style regime, BASELINE cfg #1):
+    W' is assembled in fp32 by PyTorch ops (no rounding points to reproduce), Linear layers contract as three
+    bf16 products on the engine; convolutions and unaligned shapes use the library."""
+    if x.dtype != torch.float32:
+        raise RuntimeError(f"lycoris_b200: input dtype {x.dtype} != weight dtype torch.float32 (no autocast active)")
+    plain = module._is_outermost_on_plain_forward() and not args and not kwargs
+    base = None if plain else module.org_forward(x, *args, **kwargs)
+    Wm = assemble_fallback(W)
+    if not plain:
+        Wm = Wm - W
+    b = bias if plain else None
+    if module.module_type == "linear" and _f32_supported(W) and x.shape[-1] % 8 == 0 and x.numel() > 0:
+        y = _MergedContractionF32.apply(x, Wm, b)
+    else:
+        warning_once("lycoris_b200: fp32 convolutions / unaligned fp32 layers contract through the library")
+        y = module.op(x, Wm, b, **module.kw_dict)
     return y if plain else base + y
 
 

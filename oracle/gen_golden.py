@@ -49,6 +49,22 @@ ALGOS = {
     "ia3_in": dict(cls="IA3Module", dim=4, alpha=1.0, kw={"train_on_input": True}),
     "dylora": dict(cls="DyLoraModule", dim=8, alpha=4.0, kw={"block_size": 2}),
 }
+# option variants: trainable scalar, DoRA on either axis, Tucker conv,
+# non-unit multiplier — served by the engine's PyTorch-assembled-W' path + the tcgen05 contractions
+OPTION_CASES = {
+    "locon_scalar/linear": dict(algo="locon", layer="linear", kw={"use_scalar": True}),
+    "locon_scalar/conv3": dict(algo="locon", layer="conv3", kw={"use_scalar": True}),
+    "locon_dora/linear": dict(algo="locon", layer="linear", kw={"weight_decompose": True}),
+    "locon_dora_in/linear": dict(algo="locon", layer="linear", kw={"weight_decompose": True, "wd_on_out": False}),
+    "locon_dora/conv3": dict(algo="locon", layer="conv3", kw={"weight_decompose": True}),
+    "locon_tucker/conv3": dict(algo="locon", layer="conv3", kw={}, use_tucker=True),
+    "locon_mult/linear": dict(algo="locon", layer="linear", kw={}, multiplier=0.5),
+    "lokr_dora/linear": dict(algo="lokr_full", layer="linear", kw={"weight_decompose": True}),
+    "lokr_scalar/conv3": dict(algo="lokr_lowrank", layer="conv3", kw={"use_scalar": True}),
+    "lokr_mult/linear": dict(algo="lokr_full", layer="linear", kw={}, multiplier=0.5),
+    "loha_dora/linear": dict(algo="loha", layer="linear", kw={"weight_decompose": True}),
+    "loha_scalar/linear": dict(algo="loha", layer="linear", kw={"use_scalar": True}),
+}
 REGIMES = ("fp32", "bf16", "autocast_bf16")
 
 
@@ -93,14 +109,18 @@ def oracle_inputs(algo_key, module):
     raise KeyError(algo_key)
 
 
-def run_case(algo_key, layer_key, regime, seed):
+def run_case(algo_key, layer_key, regime, seed, extra_kw=None, multiplier=1.0, use_tucker=False):
     a, spec = ALGOS[algo_key], LAYERS[layer_key]
+    a = dict(a, kw={**a["kw"], **(extra_kw or {})})
     base = make_base(spec, seed)
     cls = getattr(lycoris.modules, a["cls"], None) or getattr(
         __import__("lycoris.modules." + {"IA3Module": "ia3", "DyLoraModule": "dylora"}[a["cls"]], fromlist=["x"]), a["cls"])
     torch.manual_seed(seed + 1)
-    mod = cls("case", base, 1.0, a["dim"], a["alpha"], 0.0, 0.0, 0.0, False, **a["kw"])
+    mod = cls("case", base, multiplier, a["dim"], a["alpha"], 0.0, 0.0, 0.0, use_tucker, **a["kw"])
     perturb(mod, seed + 2)
+    if isinstance(getattr(mod, "scalar", None), nn.Parameter):
+        with torch.no_grad():
+            mod.scalar.fill_(0.7)
     g = torch.Generator().manual_seed(seed + 3)
     x = torch.randn(spec["x"], generator=g)
     ac = None
@@ -131,6 +151,12 @@ def run_case(algo_key, layer_key, regime, seed):
 
     # oracle on the same tensors
     algo, p, cfg = oracle_inputs(algo_key, mod)
+    cfg["multiplier"] = multiplier
+    cfg["wd_on_out"] = getattr(mod, "wd_on_out", True)
+    for extra in ("scalar", "dora_scale", "lora_mid.weight"):
+        named = dict(mod.named_parameters())
+        if extra in named:
+            p[extra] = named[extra]
     conv = None
     if spec["kind"] == "conv":
         conv = dict(stride=base.stride, padding=base.padding, dilation=base.dilation, groups=base.groups)
@@ -160,6 +186,7 @@ def run_case(algo_key, layer_key, regime, seed):
         "meta": {
             "algo_key": algo_key, "layer": layer_key, "regime": regime, "cls": a["cls"], "dim": a["dim"],
             "alpha": a["alpha"], "kw": a["kw"], "layer_spec": spec, "scale": float(getattr(mod, "scale", 1.0)),
+            "multiplier": multiplier, "use_tucker": use_tucker, "wd_on_out": getattr(mod, "wd_on_out", True),
             "dylora_seed": seed + 4, "dylora_b": cfg.get("b"),
         },
     }
@@ -238,6 +265,13 @@ def main():
                 cases[f"{algo_key}/{layer_key}"] = run_case(algo_key, layer_key, regime, seed)
                 n += 1
         torch.save(cases, os.path.join(OUT, f"layers_{regime}.pt"))
+        opts = {}
+        for name, oc in OPTION_CASES.items():
+            seed += 10
+            opts[name] = run_case(oc["algo"], oc["layer"], regime, seed, oc["kw"], oc.get("multiplier", 1.0),
+                                  oc.get("use_tucker", False))
+            n += 1
+        torch.save(opts, os.path.join(OUT, f"options_{regime}.pt"))
     print(f"{n} layer cases: oracle == reference (bit-exact), fixtures written")
 
     # 2b. BASELINE.json configs[0]: LoCon dim 4 alpha 1 on nn.Linear(768, 768) through the generic wrapper,

@@ -75,11 +75,38 @@ def _op(x, w, b, conv):
     return F.conv2d(x, w, b, **conv)
 
 
+def _scalar(p, like):
+    """trainable `scalar` parameter when use_scalar, else the constant-1 buffer (locon.py:150-153)."""
+    return p["scalar"] if "scalar" in p else torch.tensor(1.0, device=like.device)
+
+
 def delta_locon(p, shape, cfg):
-    """lycoris/modules/locon.py:198-219 make_weight (no tucker / dropout): up @ down, * scalar."""
+    """lycoris/modules/locon.py:198-219 make_weight (no dropout): up @ down — or the Tucker rebuild
+    einsum("i j ..., i p, j r -> p r ...") of functional/general.py:9-11 — times scalar."""
     wa, wb = p["lora_up.weight"], p["lora_down.weight"]
-    weight = wa.view(wa.size(0), -1) @ wb.view(wb.size(0), -1)
-    return weight.view(shape) * cfg.get("scalar", torch.tensor(1.0, device=weight.device))
+    if "lora_mid.weight" in p:
+        t = p["lora_mid.weight"]
+        weight = torch.einsum("i j ..., i p, j r -> p r ...", t, wa.view(wa.size(0), -1).transpose(0, 1),
+                              wb.view(wb.size(0), -1))
+    else:
+        weight = wa.view(wa.size(0), -1) @ wb.view(wb.size(0), -1)
+    return weight.view(shape) * _scalar(p, weight)
+
+
+def apply_weight_decompose(weight, dora_scale, wd_on_out, multiplier=1):
+    """DoRA rescale, lycoris/modules/locon.py:239-260 (identical copies in loha.py / lokr.py)."""
+    weight = weight.to(dora_scale.dtype)
+    dims = weight.dim() - 1
+    if wd_on_out:
+        norm = weight.reshape(weight.shape[0], -1).norm(dim=1).reshape(weight.shape[0], *[1] * dims)
+    else:
+        norm = weight.transpose(0, 1).reshape(weight.shape[1], -1).norm(dim=1, keepdim=True)
+        norm = norm.reshape(weight.shape[1], *[1] * dims).transpose(0, 1)
+    norm = norm + torch.finfo(weight.dtype).eps
+    scale = dora_scale.to(weight.device) / norm
+    if multiplier != 1:
+        scale = multiplier * (scale - 1) + 1
+    return weight * scale
 
 
 class _HadaWeight(torch.autograd.Function):
@@ -155,15 +182,26 @@ def layer_forward(algo, x, W, bias, p, cfg, conv=None):
     base_weight = W.detach()
     mult = cfg.get("multiplier", 1.0)
     shape = tuple(W.shape)
+    dora = p.get("dora_scale")
+    wd_out = cfg.get("wd_on_out", True)
     if algo == "locon":
         diff = delta_locon(p, shape, cfg).to(base_weight.dtype) * cfg["scale"]  # locon.py:322
-        new_weight = base_weight + diff * mult  # locon.py:328
+        if dora is not None:
+            new_weight = apply_weight_decompose(base_weight + diff, dora, wd_out, mult)  # locon.py:323-326
+        else:
+            new_weight = base_weight + diff * mult  # locon.py:328
     elif algo == "loha":
-        diff = delta_loha(p, shape, cfg).to(base_weight.dtype) * cfg.get("scalar", 1.0)  # loha.py:311
-        new_weight = base_weight + diff * mult  # loha.py:318
+        diff = delta_loha(p, shape, cfg).to(base_weight.dtype) * _scalar(p, base_weight)  # loha.py:311
+        if dora is not None:
+            new_weight = apply_weight_decompose(base_weight + diff, dora, wd_out, mult)  # loha.py:313-316
+        else:
+            new_weight = base_weight + diff * mult  # loha.py:318
     elif algo == "lokr":
-        diff = delta_lokr(p, shape, cfg).to(base_weight.dtype) * cfg.get("scalar", 1.0)  # lokr.py:553
-        new_weight = base_weight + diff if mult == 1 else base_weight + diff * mult  # lokr.py:559-562
+        diff = delta_lokr(p, shape, cfg).to(base_weight.dtype) * _scalar(p, base_weight)  # lokr.py:553
+        if dora is not None:
+            new_weight = apply_weight_decompose(base_weight + diff, dora, wd_out, mult)  # lokr.py:555-558
+        else:
+            new_weight = base_weight + diff if mult == 1 else base_weight + diff * mult  # lokr.py:559-562
     elif algo == "ia3":
         new_weight = merged_ia3(p, W, cfg).to(base_weight.device, dtype=base_weight.dtype)  # ia3.py:137-141
     elif algo == "dylora":

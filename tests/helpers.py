@@ -10,14 +10,15 @@ from conftest import GOLDEN
 _CACHE = {}
 
 
-def load_cases(regime):
-    if regime not in _CACHE:
-        _CACHE[regime] = torch.load(os.path.join(GOLDEN, f"layers_{regime}.pt"), weights_only=False)
-    return _CACHE[regime]
+def load_cases(regime, kind="layers"):
+    key = (kind, regime)
+    if key not in _CACHE:
+        _CACHE[key] = torch.load(os.path.join(GOLDEN, f"{kind}_{regime}.pt"), weights_only=False)
+    return _CACHE[key]
 
 
-def case_ids(regime):
-    return sorted(load_cases(regime).keys())
+def case_ids(regime, kind="layers"):
+    return sorted(load_cases(regime, kind).keys())
 
 
 def build_base(case, device="cpu"):
@@ -41,7 +42,8 @@ def build_product_module(case, base):
     meta = case["meta"]
     cls = {"LoConModule": M.LoConModule, "LohaModule": M.LohaModule, "LokrModule": M.LokrModule,
            "IA3Module": M.IA3Module, "DyLoraModule": M.DyLoraModule}[meta["cls"]]
-    mod = cls("case", base, 1.0, meta["dim"], meta["alpha"], 0.0, 0.0, 0.0, False, **meta["kw"])
+    mod = cls("case", base, meta.get("multiplier", 1.0), meta["dim"], meta["alpha"], 0.0, 0.0, 0.0,
+              meta.get("use_tucker", False), **meta["kw"])
     own = dict(mod.named_parameters())
     assert set(own) == set(case["params"]), (sorted(own), sorted(case["params"]))
     with torch.no_grad():
@@ -56,7 +58,7 @@ def oracle_args(case, device="cpu"):
     meta = case["meta"]
     key = meta["algo_key"]
     p = {k: v.to(device) for k, v in case["params"].items()}
-    cfg = {"multiplier": 1.0, "scale": meta["scale"]}
+    cfg = {"multiplier": meta.get("multiplier", 1.0), "scale": meta["scale"], "wd_on_out": meta.get("wd_on_out", True)}
     if key == "locon":
         algo = "locon"
     elif key == "loha":

@@ -20,7 +20,7 @@ Y_REL = 2.0 ** -6
 G_REL = 3e-2
 
 
-def _run_engine(case, regime):
+def _run_engine(case, regime):  # noqa: C901
     dev = "cuda"
     base = build_base(case, dev)
     mod = build_product_module(case, base).to(dev)
@@ -95,16 +95,54 @@ def test_engine_matches_oracle_on_device(regime):
         _check(name, y, dx, grads, oy, odx, ref_grads)
 
 
-def test_fp32_base_is_refused_loudly():
-    """cfg #1 regime (fp32 everywhere, no autocast) is the reference's CPU case; the engine
-    contracts 16-bit operands only and says so instead of silently down-casting."""
-    case = load_cases("fp32")["locon/linear"]
-    base = build_base(case, "cuda")
-    mod = build_product_module(case, base).cuda()
-    mod.apply_to()
-    with pytest.raises(NotImplementedError):
-        base(case["x"].cuda())
-    mod.restore()
+def test_fp32_regime_linear_cases_match_reference_fixtures():
+    """fp32 base + fp32 adapter, no autocast (cfg #1's regime): Linear layers contract as three bf16 products
+    accumulated in fp32 on the engine — checked against the reference's fp32 CPU outputs at 1e-4."""
+    from lycoris_b200.engine import _lib
+
+    cases = load_cases("fp32")
+    for name in case_ids("fp32"):
+        if not name.endswith("/linear"):
+            continue
+        case = cases[name]
+        before = _lib.launch_count()
+        y, dx, grads = _run_engine(case, "fp32")
+        assert _lib.launch_count() >= before + 9, name  # 3 contractions x 3 bf16 products
+        for tag, a_, b_ in (("y", y, case["y"]), ("dx", dx, case["dx"])):
+            err = float((a_.float().cpu() - b_.float()).abs().max())
+            assert err <= 1e-4 * max(1.0, float(b_.abs().max())), (name, tag, err)
+        for k_, g in case["grads"].items():
+            assert rel_err(grads[k_].cpu(), g) <= 1e-3, (name, k_, rel_err(grads[k_].cpu(), g))
+
+
+def test_cfg1_locon_linear768_fp32_on_gpu():
+    """BASELINE.json configs[0] in its own regime (fp32, no autocast) through the generic wrapper on the GPU."""
+    import torch.nn as nn
+
+    from helpers import load_cfg1
+    from lycoris_b200.wrapper import LycorisNetwork, create_lycoris
+
+    c = load_cfg1()
+    base = nn.Sequential(nn.Linear(768, 768))
+    base[0].weight.data = c["weight"].clone()
+    base[0].bias.data = c["bias"].clone()
+    base.cuda().requires_grad_(False)
+    LycorisNetwork.apply_preset({"target_module": ["Linear"], "target_name": []})
+    net = create_lycoris(base, 1.0, linear_dim=4, linear_alpha=1, algo="locon")
+    net.apply_to()
+    net.cuda()
+    with torch.no_grad():
+        for k_, v in net.loras[0].named_parameters():
+            v.copy_(c["params"][k_])
+    y = base(c["x"].cuda())
+    loss = y.float().pow(2).mean()
+    loss.backward()
+    net.restore()
+    assert float((y[0].detach().cpu() - c["y0"]).abs().max()) <= 1e-4 * float(c["y0"].abs().max())
+    assert abs(float(loss) - float(c["loss"])) <= 1e-5 * abs(float(c["loss"]))
+    for k_, g in c["grads"].items():
+        mine = dict(net.loras[0].named_parameters())[k_].grad.cpu()
+        assert rel_err(mine, g) <= 1e-3, (k_, rel_err(mine, g))
 
 
 def test_fp32_base_under_autocast_runs():
@@ -348,3 +386,19 @@ def test_cfg1_locon_linear768_on_gpu_under_autocast():
     for k, g in c["grads"].items():
         mine = dict(net.loras[0].named_parameters())[k].grad.cpu()
         assert rel_err(mine, g) <= 5e-2, (k, rel_err(mine, g))
+
+
+@pytest.mark.parametrize("regime", ["bf16", "autocast_bf16"])
+def test_engine_option_variants_match_reference_fixtures(regime):
+    """Trainable scalar, DoRA on either axis, Tucker conv, multiplier 0.5: W' is assembled by PyTorch ops
+    following the reference's sequence and the three contractions run on the engine; outputs and every
+    parameter gradient (incl. scalar / dora_scale / lora_mid) against the reference fixtures."""
+    from lycoris_b200.engine import _lib
+
+    cases = load_cases(regime, "options")
+    for name in case_ids(regime, "options"):
+        case = cases[name]
+        before = _lib.launch_count()
+        y, dx, grads = _run_engine(case, regime)
+        assert _lib.launch_count() > before, name
+        _check(name, y, dx, grads, case["y"], case["dx"], case["grads"])
