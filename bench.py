@@ -312,12 +312,56 @@ def run_engine(args):
     if args.kernel_table and rank == 0:
         from torch.profiler import ProfilerActivity, profile
 
-        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
-            step()
-            torch.cuda.synchronize()
+        from torch.profiler import record_function
+
+        from lycoris_b200.engine import ops as _ops
+
+        def _labelled(fn, label):
+            def wrapped(*a, **k):
+                with record_function(label):
+                    return fn(*a, **k)
+            return staticmethod(wrapped)
+
+        saved = {}
+        for cls in (_ops._AdapterContraction, _ops._MergedContraction):
+            saved[cls] = (cls.forward, cls.backward)
+            cls.forward = _labelled(cls.forward, "lyco_node_fwd")
+            cls.backward = _labelled(cls.backward, "lyco_node_bwd")
+        try:
+            with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+                step()
+                torch.cuda.synchronize()
+        finally:
+            for cls, (f, b) in saved.items():
+                cls.forward, cls.backward = staticmethod(f), staticmethod(b)
+        # attribute every kernel to "inside an engine autograd node" or "model side" via the CPU op that launched it
+        inside, outside = {}, {}
+        for ev in prof.events():
+            ks = getattr(ev, "kernels", None)
+            if not ks:
+                continue
+            anc, tag = ev, None
+            while anc is not None:
+                if anc.name in ("lyco_node_fwd", "lyco_node_bwd"):
+                    tag = anc.name
+                    break
+                anc = anc.cpu_parent
+            for k in ks:
+                name = k.name.split("<")[0][:70]
+                dst = inside if tag else outside
+                a = dst.setdefault(name, [0, 0.0])
+                a[0] += 1
+                a[1] += k.duration
+        with open(args.kernel_table + ".attribution", "w") as fh:
+            for title, d in (("launched inside the engine's autograd nodes", inside), ("model side (outside)", outside)):
+                tot_d = sum(v[1] for v in d.values())
+                fh.write(f"{title}: {tot_d / 1e3:.2f} ms\n")
+                for name, (cnt, t) in sorted(d.items(), key=lambda kv: -kv[1][1])[:14]:
+                    fh.write(f"{t / 1e3:10.3f} ms {cnt:6d}  {name}\n")
         agg = {}
         for ev in prof.events():
-            if ev.device_type is not None and str(ev.device_type).endswith("CUDA") and ev.device_time_total > 0:
+            if (ev.device_type is not None and str(ev.device_type).endswith("CUDA") and ev.device_time_total > 0
+                    and not ev.name.startswith("lyco_node_")):
                 name = ev.name.split("<")[0][:90]
                 a = agg.setdefault(name, [0, 0.0])
                 a[0] += 1

@@ -28,10 +28,11 @@
 extern "C" {
 #endif
 
-#define LYCO_ABI_VERSION 1
+#define LYCO_ABI_VERSION 2
 
 /* element types */
 enum { LYCO_BF16 = 0, LYCO_F16 = 1, LYCO_F32 = 2 };
+enum { LYCO_NHWC = 0, LYCO_NCHW = 1 }; /* activation layouts of the convolution output */
 
 /* adapter algorithms — lycoris/wrapper.py:45-55 network_module_dict keys */
 enum {
@@ -108,7 +109,20 @@ int lyco_gemm(const void* A, int a_mn_major, int64_t lda,
  */
 int lyco_conv2d_fprop(const void* X, const void* Wk, void* Y, const void* bias, int bias_dtype,
                       int Nb, int H, int W, int C, int O, int R, int S, int pad_h, int pad_w,
-                      int stride, int dtype, void* stream);
+                      int stride, int dtype, int y_layout, void* stream);
+/*   y_layout: LYCO_NHWC, or LYCO_NCHW — the epilogue writes Y as [Nb, O, P, Q] (PyTorch's default
+ *   layout, what F.conv2d returns for an NCHW input) with channel-major TMA stores; needs P*Q % 32 == 0. */
+
+/*
+ * dst[b][c][r] = cast(src[b][r][c]) for b < batch: the activation layout pass in front of the im2col
+ * producer.  NCHW -> NHWC is (rows = C, cols = H*W), NHWC -> NCHW is (rows = H*W, cols = C).
+ * src_dtype: LYCO_F32 (fused autocast cast, round-to-nearest-even like Tensor.to) or == dst_dtype;
+ * dst_dtype: LYCO_BF16 / LYCO_F16.
+ * Replaces the `input.to(autocast dtype)` copy autocast inserts in front of F.conv2d
+ * (lycoris/modules/locon.py:317,331 run under torch.autocast in kohya training).
+ */
+int lyco_transpose_cast(const void* src, void* dst, int batch, int rows, int cols, int src_dtype,
+                        int dst_dtype, void* stream);
 
 /*
  * dW[o, r, s, c] (fp32, [O, R*S*C]) = sum_{n,p,q} dY[n,p,q,o] * X[n, p*stride - pad_h + r, q*stride - pad_w + s, c]

@@ -65,7 +65,7 @@ conv_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_a);
     ptx::prefetch_tmap(&tmap_b);
-    if (EPI == EPI_STORE16) ptx::prefetch_tmap(&tmap_c);
+    if (epi_uses_tma(EPI)) ptx::prefetch_tmap(&tmap_c);
   }
   gemm_setup<false>(full_bar, empty_bar, tfull_bar, tempty_bar, tmem_slot, stages, warp, lane);
   const uint32_t tmem_base = *tmem_slot;
@@ -179,7 +179,7 @@ conv_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-    if (EPI == EPI_STORE16 && lane == 0) ptx::tma_store_wait_read<0>();
+    if (epi_uses_tma(EPI) && lane == 0) ptx::tma_store_wait_read<0>();
   }
 
   gemm_teardown<false>(tmem_base, warp);

@@ -44,7 +44,8 @@ constexpr int GEMM_EPI_BYTES = 4 * 2 * 2048;   // 4 epilogue warps x 2 staging b
 constexpr int GEMM_TMEM_COLS = 512;            // two accumulator stages at columns 0 and 256
 constexpr int GEMM_SMEM_BYTES = GEMM_RING_BYTES + GEMM_EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
-enum { EPI_STORE16 = 0, EPI_STORE_F32 = 1, EPI_ATOMIC_F32 = 2 };
+enum { EPI_STORE16 = 0, EPI_STORE_F32 = 1, EPI_ATOMIC_F32 = 2, EPI_STORE16_NCHW = 3 };
+__host__ __device__ constexpr bool epi_uses_tma(int epi) { return epi == EPI_STORE16 || epi == EPI_STORE16_NCHW; }
 
 struct GemmParams {
   void* C;
@@ -56,6 +57,7 @@ struct GemmParams {
   int stages;       // smem ring depth for this block_n
   int fmt;          // operand / 16-bit output format: 0 = f16, 1 = bf16
   int bias_dtype;   // LYCO_BF16 / LYCO_F16 / LYCO_F32
+  int epi_pq;       // EPI_STORE16_NCHW: output pixels per image (rows of C are (image, pixel); multiple of 32)
 };
 
 __device__ __forceinline__ float load_scalar(const void* p, int dtype, int64_t i) {
@@ -172,6 +174,37 @@ __device__ __forceinline__ void store_chunk_tma(const uint32_t (&r)[32], int row
   buf ^= 1;
 }
 
+// Same chunk written channel-major: the convolution's output as NCHW.  Rows of the tile are output pixels of ONE
+// image (epi_pq % 32 == 0), so the staging tile is [32 channels][32 pixels] (64 B per channel) and one 3-D TMA
+// store (pixel, channel, image) writes 32 contiguous pixels of each channel.
+__device__ __forceinline__ void store_chunk_tma_nchw(const uint32_t (&r)[32], int row0, int col0, const GemmParams& p,
+                                                     int n_limit, const CUtensorMap* tmap_c, uint8_t* stage, int& buf,
+                                                     int lane) {
+  if (col0 >= n_limit || row0 >= p.M) return;
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  add_bias32(v, p, col0, n_limit);
+  if (lane == 0) ptx::tma_store_wait_read<1>();
+  __syncwarp();
+  uint8_t* tile = stage + buf * 2048;
+  const uint32_t base = ptx::smem_u32(tile) + lane * 2;
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    const uint32_t pk = pack16(v[j], v[j + 1], p.fmt);
+    asm volatile("st.shared.b16 [%0], %1;" ::"r"(base + j * 64), "h"(static_cast<uint16_t>(pk & 0xffffu)) : "memory");
+    asm volatile("st.shared.b16 [%0], %1;" ::"r"(base + (j + 1) * 64), "h"(static_cast<uint16_t>(pk >> 16)) : "memory");
+  }
+  ptx::fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    const int img = row0 / p.epi_pq;
+    ptx::tma_store_3d(tmap_c, tile, row0 - img * p.epi_pq, col0, img);
+    ptx::tma_store_commit();
+  }
+  buf ^= 1;
+}
+
 template <bool PAIR>
 __device__ __forceinline__ void gemm_setup(uint64_t* full_bar, uint64_t* empty_bar, uint64_t* tfull_bar,
                                            uint64_t* tempty_bar, uint32_t* tmem_slot, int stages, int warp, int lane) {
@@ -250,6 +283,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(uint32_t t_row, int row0, int
     }
     const int col0 = col_base + c * 32;
     if (EPI == EPI_STORE16) store_chunk_tma(r, row0, col0, p, n_limit, tmap_c, stage, buf, lane);
+    else if (EPI == EPI_STORE16_NCHW) store_chunk_tma_nchw(r, row0, col0, p, n_limit, tmap_c, stage, buf, lane);
     else store_chunk_f32<EPI>(r, row0 + lane, col0, p, n_limit);
   }
 }
@@ -280,7 +314,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_a);
     ptx::prefetch_tmap(&tmap_b);
-    if (EPI == EPI_STORE16) ptx::prefetch_tmap(&tmap_c);
+    if (epi_uses_tma(EPI)) ptx::prefetch_tmap(&tmap_c);
   }
   gemm_setup<PAIR>(full_bar, empty_bar, tfull_bar, tempty_bar, tmem_slot, stages, warp, lane);
   const uint32_t tmem_base = *tmem_slot;
@@ -387,7 +421,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-    if (EPI == EPI_STORE16 && lane == 0) ptx::tma_store_wait_read<0>();  // staging smem must outlive the stores
+    if (epi_uses_tma(EPI) && lane == 0) ptx::tma_store_wait_read<0>();  // staging smem must outlive the stores
   }
 
   gemm_teardown<PAIR>(tmem_base, warp);

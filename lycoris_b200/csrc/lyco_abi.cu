@@ -13,6 +13,7 @@
 #include "conv_sm100.cuh"
 #include "gemm_sm100.cuh"
 #include "weight_kernels.cuh"
+#include "layout_kernels.cuh"
 
 namespace {
 
@@ -147,6 +148,23 @@ int make_tmap_c(CUtensorMap* m, const void* base, uint64_t N, uint64_t M, uint64
   if (r != CUDA_SUCCESS)
     return fail("cuTensorMapEncodeTiled (C) failed (%d): base=%p N=%llu M=%llu ld=%llu", static_cast<int>(r), base,
                 (unsigned long long)N, (unsigned long long)M, (unsigned long long)ld_elems);
+  return 0;
+}
+
+// C tensor map for the NCHW epilogue of the convolution: (pixel, channel, image), boxes of 32 pixels x 32 channels
+int make_tmap_c_nchw(CUtensorMap* m, const void* base, uint64_t PQ, uint64_t O, uint64_t Nb) {
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return fail("cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t gdim[3] = {PQ, O, Nb};
+  cuuint64_t gstr[2] = {PQ * 2, O * PQ * 2};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail("cuTensorMapEncodeTiled (C, NCHW) failed (%d): base=%p PQ=%llu O=%llu Nb=%llu", static_cast<int>(r),
+                base, (unsigned long long)PQ, (unsigned long long)O, (unsigned long long)Nb);
   return 0;
 }
 
@@ -404,6 +422,7 @@ int lyco_gemm(const void* A, int a_mn_major, int64_t lda, const void* B, int b_m
   p.block_n = bn; p.stages = stages_for(tc.pair, bn);
   p.fmt = (ab_dtype == LYCO_BF16) ? 1 : 0;
   p.bias_dtype = bias_dtype;
+  p.epi_pq = 0;
 
   int epi = lyco::EPI_STORE16;
   if (c_dtype == LYCO_F32) {
@@ -425,9 +444,10 @@ int lyco_gemm(const void* A, int a_mn_major, int64_t lda, const void* B, int b_m
 
 int lyco_conv2d_fprop(const void* X, const void* Wk, void* Y, const void* bias, int bias_dtype, int Nb, int H,
                       int W, int C, int O, int R, int S, int pad_h, int pad_w, int stride, int dtype,
-                      void* stream_) {
+                      int y_layout, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!X || !Wk || !Y) return fail("lyco_conv2d_fprop: null operand");
+  if (y_layout != LYCO_NHWC && y_layout != LYCO_NCHW) return fail("lyco_conv2d_fprop: bad y_layout %d", y_layout);
   if (dtype != LYCO_BF16 && dtype != LYCO_F16) return fail("lyco_conv2d_fprop: operands must be bf16/f16");
   if (C % 64 || O % 8) return fail("lyco_conv2d_fprop: needs C %% 64 == 0 and O %% 8 == 0 (C=%d O=%d)", C, O);
   if (stride < 1 || stride > 8 || R < 1 || S < 1) return fail("lyco_conv2d_fprop: bad geometry");
@@ -457,8 +477,12 @@ int lyco_conv2d_fprop(const void* X, const void* Wk, void* Y, const void* bias, 
   CUtensorMap ta, tb, tcm;
   if (make_tmap_im2col(&ta, X, Nb, H, W, C, R, S, pad_h, pad_w, stride, 128)) return 1;
   if (make_tmap(&tb, Wk, K, O, K, 64, bn)) return 1;
-  if (make_tmap_c(&tcm, Y, O, M, O)) return 1;
+  if (y_layout == LYCO_NCHW) {
+    if ((P * Q) % 32) return fail("lyco_conv2d_fprop: NCHW output needs P*Q %% 32 == 0 (P*Q=%d)", P * Q);
+    if (make_tmap_c_nchw(&tcm, Y, static_cast<uint64_t>(P) * Q, O, Nb)) return 1;
+  } else if (make_tmap_c(&tcm, Y, O, M, O)) return 1;
   lyco::ConvParams cp;
+  cp.g.epi_pq = P * Q;
   cp.g.C = Y; cp.g.bias = bias; cp.g.ldc = O; cp.g.M = M; cp.g.N = O; cp.g.K = K;
   cp.g.m_tiles = cdiv(M, 128); cp.g.n_tiles = cdiv(O, bn); cp.g.splits = 1; cp.g.k_blocks = R * S * (C / 64);
   cp.g.block_n = bn; cp.g.stages = stages_for(false, bn);
@@ -467,7 +491,35 @@ int lyco_conv2d_fprop(const void* X, const void* Wk, void* Y, const void* bias, 
   cp.low_w = -pad_w; cp.low_h = -pad_h; cp.tiles_per_tap = 1;
   const long total = static_cast<long>(cp.g.m_tiles) * cp.g.n_tiles;
   const int grid = static_cast<int>(total < di.sms ? total : di.sms);
+  if (y_layout == LYCO_NCHW) return launch_conv<lyco::MODE_FPROP, lyco::EPI_STORE16_NCHW>(ta, tb, tcm, cp, grid, stream);
   return launch_conv<lyco::MODE_FPROP, lyco::EPI_STORE16>(ta, tb, tcm, cp, grid, stream);
+}
+
+int lyco_transpose_cast(const void* src, void* dst, int batch, int rows, int cols, int src_dtype, int dst_dtype,
+                        void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!src || !dst) return fail("lyco_transpose_cast: null operand");
+  if (batch < 1 || rows < 1 || cols < 1) return fail("lyco_transpose_cast: empty tensor");
+  if (dst_dtype != LYCO_BF16 && dst_dtype != LYCO_F16) return fail("lyco_transpose_cast: dst must be bf16/f16");
+  if (src_dtype != LYCO_F32 && src_dtype != dst_dtype)
+    return fail("lyco_transpose_cast: src must be f32 or the dst dtype (src=%d dst=%d)", src_dtype, dst_dtype);
+  if ((reinterpret_cast<uintptr_t>(src) & 7) || (reinterpret_cast<uintptr_t>(dst) & 3))
+    return fail("lyco_transpose_cast: pointers must be 8-byte (src) / 4-byte (dst) aligned");
+  const int gx = cdiv(cols, lyco::TR_TILE), gy = cdiv(rows, lyco::TR_TILE);
+  if (gy > 65535 || batch > 65535) return fail("lyco_transpose_cast: rows / batch too large for one launch");
+  DeviceInfo di;
+  if (device_info(&di)) return 1;
+  const dim3 grid(gx, gy, batch), block(32, 8);
+  const int fmt = (dst_dtype == LYCO_BF16) ? 1 : 0;
+  if (src_dtype == LYCO_F32)
+    lyco::transpose_cast_kernel<float><<<grid, block, 0, stream>>>(static_cast<const float*>(src),
+                                                                  static_cast<uint16_t*>(dst), rows, cols, fmt);
+  else
+    lyco::transpose_cast_kernel<uint16_t><<<grid, block, 0, stream>>>(static_cast<const uint16_t*>(src),
+                                                                     static_cast<uint16_t*>(dst), rows, cols, fmt);
+  LYCO_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
 }
 
 int lyco_conv2d_wgrad(const void* X, const void* dY, float* dW, int Nb, int H, int W, int C, int O, int R, int S,

@@ -26,6 +26,7 @@ EXPORTED_SYMBOLS = (
     "lyco_gemm",
     "lyco_conv2d_fprop",
     "lyco_conv2d_wgrad",
+    "lyco_transpose_cast",
     "lyco_merge_weight",
     "lyco_factor_grads",
     "lyco_grad_prep",
@@ -90,8 +91,10 @@ def _bind(lib):
     lib.lyco_conv2d_fprop.argtypes = [
         c_void_p, c_void_p, c_void_p, c_void_p, c_int,  # X Wk Y bias bias_dtype
         c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,  # Nb H W C O R S pad_h pad_w stride
-        c_int, c_void_p,  # dtype stream
+        c_int, c_int, c_void_p,  # dtype y_layout stream
     ]
+    lib.lyco_transpose_cast.restype = c_int
+    lib.lyco_transpose_cast.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
     lib.lyco_conv2d_wgrad.restype = c_int
     lib.lyco_conv2d_wgrad.argtypes = [
         c_void_p, c_void_p, c_void_p,  # X dY dW
@@ -125,7 +128,7 @@ def load():
     except OSError as e:  # pragma: no cover - depends on the box
         raise EngineUnavailable(f"lycoris_b200: cannot load {LIB_PATH}: {e}") from e
     _lib = _bind(lib)
-    if _lib.lyco_abi_version() != 1:
+    if _lib.lyco_abi_version() != 2:
         raise EngineUnavailable("lycoris_b200: ABI version mismatch between _lib.py and the .so")
     return _lib
 

@@ -5,6 +5,7 @@ hand-written sm_100a kernels."""
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 
@@ -110,24 +111,52 @@ def conv2d_supported(x, weight_shape, stride, padding, dilation, groups, dtype=N
     return C % 64 == 0 and O % 8 == 0
 
 
-def as_nhwc(x):
-    """channels_last view of ``x`` (a transpose copy only if it is not already NHWC in memory)."""
-    return x if x.is_contiguous(memory_format=torch.channels_last) else x.contiguous(memory_format=torch.channels_last)
+# debugging knobs: LYCO_LAYOUT_PASS=torch does the NCHW -> NHWC pass with Tensor.to; LYCO_CONV_OUT=nhwc keeps the
+# convolution output channels_last even for NCHW inputs
+_ENGINE_LAYOUT_PASS = os.environ.get("LYCO_LAYOUT_PASS", "engine") != "torch"
+_NCHW_EPILOGUE = os.environ.get("LYCO_CONV_OUT", "auto") != "nhwc"
 
 
-def conv2d_fprop(x, wk, bias, R, S, pad, stride):
+def as_nhwc(x, dtype=None):
+    """``x`` [Nb, C, H, W] in channels_last storage and ``dtype`` (default: its own).  Already-NHWC tensors of
+    that dtype pass through; a contiguous NCHW tensor (fp32 or the target dtype) goes through ONE engine pass
+    that transposes and casts together (lyco_transpose_cast) — this is the copy autocast would make anyway."""
+    dtype = dtype or x.dtype
+    if x.dtype == dtype and x.is_contiguous(memory_format=torch.channels_last):
+        return x
+    if (_ENGINE_LAYOUT_PASS and x.is_cuda and x.is_contiguous() and dtype in (torch.bfloat16, torch.float16)
+            and x.dtype in (torch.float32, dtype) and x.numel() > 0 and x.shape[0] < 65536):
+        Nb, C, H, W = x.shape
+        out = torch.empty((Nb, C, H, W), device=x.device, dtype=dtype, memory_format=torch.channels_last)
+        rc = _lib.load().lyco_transpose_cast(_ptr(x), _ptr(out), Nb, C, H * W, dtype_code(x.dtype),
+                                             dtype_code(dtype), _stream())
+        _lib.check(rc, "transpose_cast")
+        return out
+    # any other striding (channel slices of a concatenation, expanded tensors, ...): one strided copy into a DENSE
+    # NHWC buffer.  Not Tensor.to(memory_format=...): that returns `self` for a non-dense tensor whose strides
+    # merely look channels-last.
+    out = torch.empty(x.shape, device=x.device, dtype=dtype, memory_format=torch.channels_last)
+    return out.copy_(x)
+
+
+def conv2d_fprop(x, wk, bias, R, S, pad, stride, out_nchw=False):
     """``x``: [Nb, C, H, W] in channels_last storage; ``wk``: [O, R*S*C] (filter as [O,R,S,C]).
-    Returns y [Nb, O, P, Q] in channels_last storage."""
+    Returns y [Nb, O, P, Q]: channels_last storage, or plain contiguous NCHW with ``out_nchw`` (written
+    channel-major by the epilogue; needs P*Q % 32 == 0, otherwise the NHWC result is returned)."""
     _require_cuda(x, wk, bias)
     x = as_nhwc(x)
     Nb, C, H, W = x.shape
     O = wk.shape[0]
     P = (H + 2 * pad[0] - R) // stride + 1
     Q = (W + 2 * pad[1] - S) // stride + 1
-    y = torch.empty((Nb, O, P, Q), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+    nchw = bool(out_nchw) and _NCHW_EPILOGUE and (P * Q) % 32 == 0
+    if nchw:
+        y = torch.empty((Nb, O, P, Q), device=x.device, dtype=x.dtype)
+    else:
+        y = torch.empty((Nb, O, P, Q), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
     rc = _lib.load().lyco_conv2d_fprop(
         _ptr(x), _ptr(wk), _ptr(y), _ptr(bias), dtype_code(bias.dtype) if bias is not None else 0,
-        Nb, H, W, C, O, R, S, pad[0], pad[1], stride, dtype_code(x.dtype), _stream())
+        Nb, H, W, C, O, R, S, pad[0], pad[1], stride, dtype_code(x.dtype), 1 if nchw else 0, _stream())
     _lib.check(rc, "conv2d_fprop")
     return y
 

@@ -157,26 +157,38 @@ def _conv_engine_ok(x, w, cp, dtype=None):
 
 
 def _conv_forward(x, w, bias, cp):
-    if _conv_engine_ok(x, w, cp):
+    """(y, x_saved, info) — on the engine the input goes through ONE layout pass (NCHW -> NHWC fused with the
+    autocast cast; nothing if it already is NHWC) and the output comes back in the input's layout, written
+    directly by the epilogue.  ``x_saved`` (NHWC, 16-bit) is what the weight-gradient kernel reads again."""
+    if _conv_engine_ok(x, w, cp, w.dtype):
         O, C, R, S = w.shape
+        nchw_in = not x.is_contiguous(memory_format=torch.channels_last)
+        xs = K.as_nhwc(x, w.dtype)
         wk = w.permute(0, 2, 3, 1).reshape(O, R * S * C)  # filter taps outermost, channels contiguous
-        return K.conv2d_fprop(x, wk, bias, R, S, cp["padding"], cp["stride"][0])
-    return torch.ops.aten.convolution(x, w, bias, cp["stride"], cp["padding"], cp["dilation"], False,
-                                      [0] * len(cp["stride"]), cp["groups"])
+        y = K.conv2d_fprop(xs, wk, bias, R, S, cp["padding"], cp["stride"][0], out_nchw=nchw_in)
+        return y, xs, (True, nchw_in, x.dtype)
+    xd = x.dtype
+    if x.dtype != w.dtype:
+        x = x.to(w.dtype)
+    y = torch.ops.aten.convolution(x, w, bias, cp["stride"], cp["padding"], cp["dilation"], False,
+                                   [0] * len(cp["stride"]), cp["groups"])
+    return y, x, (False, False, xd)
 
 
-def _conv_backward(dy, x, w, cp, need_x, need_w):
-    """(dx, dw) with dw shaped like ``w`` (fp32 from the engine, w.dtype from the library path)."""
-    if _conv_engine_ok(x, w, cp):
+def _conv_backward(dy, x, w, cp, info, need_x, need_w):
+    """(dx, dw) with dw shaped like ``w`` (fp32 from the engine, w.dtype from the library path); dx in the
+    layout and dtype of the forward input."""
+    engine, nchw_in, x_dtype = info
+    dx = dw = None
+    if engine:
         O, C, R, S = w.shape
         st, pad = cp["stride"][0], cp["padding"]
-        dyc = K.as_nhwc(dy)
-        dx = dw = None
+        dyc = K.as_nhwc(dy, w.dtype)
         if need_x:
             if st == 1 and O % 64 == 0 and C % 8 == 0 and pad[0] <= R - 1 and pad[1] <= S - 1:
                 # input gradient = the same implicit GEMM over dY with the flipped, transposed filter
                 wd = w.flip(2, 3).permute(1, 2, 3, 0).reshape(C, R * S * O)
-                dx = K.conv2d_fprop(dyc, wd, None, R, S, (R - 1 - pad[0], S - 1 - pad[1]), 1)
+                dx = K.conv2d_fprop(dyc, wd, None, R, S, (R - 1 - pad[0], S - 1 - pad[1]), 1, out_nchw=nchw_in)
             else:
                 dx = torch.ops.aten.convolution_backward(
                     dyc, x, w, None, cp["stride"], cp["padding"], cp["dilation"], False, [0, 0], cp["groups"],
@@ -184,10 +196,12 @@ def _conv_backward(dy, x, w, cp, need_x, need_w):
         if need_w:
             dwk = K.conv2d_wgrad(x, dyc, R, S, pad, st)  # [O, R*S*C] fp32
             dw = dwk.view(O, R, S, C).permute(0, 3, 1, 2).contiguous()
-        return dx, dw
-    dx, dw, _ = torch.ops.aten.convolution_backward(
-        dy, x, w, None, cp["stride"], cp["padding"], cp["dilation"], False, [0] * len(cp["stride"]),
-        cp["groups"], [need_x, need_w, False])
+    else:
+        dx, dw, _ = torch.ops.aten.convolution_backward(
+            dy.contiguous(), x, w, None, cp["stride"], cp["padding"], cp["dilation"], False,
+            [0] * len(cp["stride"]), cp["groups"], [need_x, need_w, False])
+    if dx is not None and dx.dtype != x_dtype:
+        dx = dx.to(x_dtype)
     return dx, dw
 
 
@@ -277,9 +291,7 @@ class _AdapterContraction(torch.autograd.Function):
                 x2 = x2.contiguous()
             y = _dense_nt(x2, Wm, bias).view(*x.shape[:-1], out_dim)
         else:
-            if _conv_engine_ok(x, Wm, conv):
-                x = K.as_nhwc(x)  # one transpose at most; the NHWC copy is what backward's wgrad reads again
-            y = _conv_forward(x, Wm, bias, conv)
+            y, x, ctx.conv_info = _conv_forward(x, Wm, bias, conv)
         ctx.save_for_backward(x, W, Wm, *factors)
         ctx.spec, ctx.conv, ctx.ac_dtype = spec, conv, ac_dtype
         ctx.dims = (out_dim, in_dim)
@@ -306,8 +318,7 @@ class _AdapterContraction(torch.autograd.Function):
                     x2 = x2.contiguous()
                 dWm = _dense_tn_f32(dy2, x2)
         else:
-            dyc = dy.contiguous()
-            dx, dw = _conv_backward(dyc, x, Wm, conv, need_x, need_f)
+            dx, dw = _conv_backward(dy, x, Wm, conv, ctx.conv_info, need_x, need_f)
             if need_f:
                 dWm = dw.reshape(out_dim, in_dim).float()
         grads = [None] * len(factors)
@@ -337,9 +348,7 @@ class _MergedContraction(torch.autograd.Function):
                 x2 = x2.contiguous()
             y = _dense_nt(x2, Wm.contiguous(), bias).view(*x.shape[:-1], Wm.shape[0])
         else:
-            if _conv_engine_ok(x, Wm, conv):
-                x = K.as_nhwc(x)
-            y = _conv_forward(x, Wm, bias, conv)
+            y, x, ctx.conv_info = _conv_forward(x, Wm, bias, conv)
         ctx.save_for_backward(x, Wm)
         ctx.conv = conv
         return y
@@ -362,7 +371,7 @@ class _MergedContraction(torch.autograd.Function):
                     x2 = x2.contiguous()
                 dw = _dense_tn_f32(dy2, x2).to(Wm.dtype)
         else:
-            dx, dw = _conv_backward(dy.contiguous(), x, Wm, conv, need_x, need_w)
+            dx, dw = _conv_backward(dy, x, Wm, conv, ctx.conv_info, need_x, need_w)
             if dw is not None and dw.dtype != Wm.dtype:
                 dw = dw.to(Wm.dtype)
         return dx, dw, None, None
@@ -410,11 +419,11 @@ def adapter_forward(module, x, args, kwargs, native_spec, assemble_fallback):
     if x.dtype != cdt:
         if ac is None:
             raise RuntimeError(f"lycoris_b200: input dtype {x.dtype} != weight dtype {cdt} (no autocast active)")
-        if is_conv and x.dim() == 4 and _conv_engine_ok(x, W, conv, cdt):
-            # autocast cast fused with the NCHW -> NHWC transpose the im2col producer needs (one pass, not two)
-            x = x.to(cdt, memory_format=torch.channels_last)
-        else:
+        pointwise_nhwc = (is_conv and x.dim() == 4 and _is_pointwise(conv, W)
+                          and x.is_contiguous(memory_format=torch.channels_last))
+        if pointwise_nhwc or not (is_conv and x.dim() == 4 and _conv_engine_ok(x, W, conv, cdt)):
             x = x.to(cdt)
+        # else: the convolution node casts and transposes to NHWC in one engine pass (lyco_transpose_cast)
     if is_conv and _is_pointwise(conv, W) and x.is_contiguous(memory_format=torch.channels_last) and x.dim() == 4:
         # NHWC 1x1 convolution is a plain linear over channels: run it on the tcgen05 GEMM
         y = adapter_forward_pointwise(module, x, W, bias, ac, native_spec, assemble_fallback, args, kwargs)

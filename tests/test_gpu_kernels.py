@@ -155,3 +155,39 @@ def test_lowrank_merge_and_grads(algo, r):
     gs = k.factor_grads(d, dW, None, [t.shape for t in f])
     for g, t in zip(gs, fr):
         assert float((g - t.grad).abs().max()) <= 2e-3 * float(t.grad.abs().max())
+
+
+@pytest.mark.parametrize("Nb,C,H,W", [(2, 64, 8, 8), (3, 320, 16, 16), (1, 5, 7, 9), (2, 130, 3, 33), (8, 640, 64, 64)])
+@pytest.mark.parametrize("src_dtype", [torch.float32, torch.bfloat16, torch.float16])
+def test_transpose_cast_is_bit_exact(Nb, C, H, W, src_dtype):
+    """lyco_transpose_cast == Tensor.to(dtype, memory_format=channels_last), including ragged tiles."""
+    from lycoris_b200.engine import kernels as K
+
+    torch.manual_seed(C * H + W)
+    x = torch.randn(Nb, C, H, W, device="cuda", dtype=src_dtype)
+    dst = torch.bfloat16 if src_dtype != torch.float16 else torch.float16
+    before = K._lib.launch_count()
+    got = K.as_nhwc(x, dst)
+    assert K._lib.launch_count() == before + 1
+    want = x.to(dst).contiguous(memory_format=torch.channels_last)
+    assert got.dtype == dst and got.shape == x.shape and got.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(got, want)
+    assert K.as_nhwc(got, dst) is got  # already NHWC: no pass at all
+
+
+@pytest.mark.parametrize("Nb,C,O,H,W,stride", [(2, 64, 64, 8, 8, 1), (1, 128, 200, 16, 16, 1), (2, 64, 96, 16, 16, 2)])
+def test_conv_fprop_nchw_epilogue_equals_nhwc(Nb, C, O, H, W, stride):
+    """The channel-major TMA-store epilogue writes the same numbers as the NHWC one (bit-exact), with bias."""
+    from lycoris_b200.engine import kernels as K
+
+    torch.manual_seed(O + H)
+    x = torch.randn(Nb, C, H, W, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    wk = (torch.randn(O, 9 * C, device="cuda") * 0.05).to(torch.bfloat16)
+    bias = torch.randn(O, device="cuda", dtype=torch.bfloat16)
+    a = K.conv2d_fprop(x, wk, bias, 3, 3, (1, 1), stride)
+    b = K.conv2d_fprop(x, wk, bias, 3, 3, (1, 1), stride, out_nchw=True)
+    assert a.is_contiguous(memory_format=torch.channels_last) and b.is_contiguous()
+    assert torch.equal(a.contiguous(), b)
+    ref = torch.nn.functional.conv2d(x.float(), wk.view(O, 3, 3, C).permute(0, 3, 1, 2).float(), bias.float(),
+                                     stride, 1)
+    assert float((b.float() - ref).abs().max()) <= 2e-2 * float(ref.abs().max())

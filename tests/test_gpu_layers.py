@@ -230,8 +230,9 @@ CONV_ENGINE_CASES = [
 ]
 
 
+@pytest.mark.parametrize("layout", ["nhwc", "nchw", "nchw_fp32"])
 @pytest.mark.parametrize("algo,Nb,C,O,H,W,k,stride", CONV_ENGINE_CASES)
-def test_conv_implicit_gemm_layer_matches_oracle(algo, Nb, C, O, H, W, k, stride):
+def test_conv_implicit_gemm_layer_matches_oracle(algo, Nb, C, O, H, W, k, stride, layout):
     """3x3 convolutions on channels_last activations run the TMA-im2col implicit GEMM (fprop, dgrad as
     fprop on dY with the flipped filter, wgrad) — compared with the oracle (cuDNN eager) on device."""
     import torch.nn as nn
@@ -259,7 +260,11 @@ def test_conv_implicit_gemm_layer_matches_oracle(algo, Nb, C, O, H, W, k, stride
         with torch.no_grad():
             mod.hada_w2_a.normal_(0, 0.1)
         oalgo, cfg = "loha", {"scale": mod.scale, "multiplier": 1.0}
-    x = torch.randn(Nb, C, H, W, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    # nhwc: activations already channels_last; nchw: PyTorch's default layout (one engine transpose pass in, the
+    # epilogue writes NCHW out); nchw_fp32: fp32 input under autocast, cast fused into that transpose pass
+    x = torch.randn(Nb, C, H, W, device="cuda", dtype=torch.float32 if layout == "nchw_fp32" else torch.bfloat16)
+    if layout == "nhwc":
+        x = x.contiguous(memory_format=torch.channels_last)
     x.requires_grad_(True)
     before = _lib.launch_count()
     mod.apply_to()
@@ -269,10 +274,19 @@ def test_conv_implicit_gemm_layer_matches_oracle(algo, Nb, C, O, H, W, k, stride
     y.backward(dy)
     mod.restore()
     engine_dgrad = stride == 1 and O % 64 == 0
-    assert _lib.launch_count() - before >= (5 if engine_dgrad else 4)  # merge + fprop + (dgrad) + wgrad + factor grads
+    nhwc = lambda t: t.is_contiguous(memory_format=torch.channels_last)  # noqa: E731
+    layout_passes = int(not nhwc(x)) + int(not nhwc(dy))  # one engine transpose(+cast) pass per NCHW operand
+    # merge + fprop + (dgrad) + wgrad + factor grads (+ layout passes)
+    assert _lib.launch_count() - before >= (5 if engine_dgrad else 4) + layout_passes
+    assert y.dtype == torch.bfloat16 and x.grad.dtype == x.dtype and x.grad.shape == x.shape
+    if layout != "nhwc" and (y.shape[2] * y.shape[3]) % 32 == 0:
+        assert y.is_contiguous(), "NCHW in -> NCHW out (written by the epilogue)"
+        if engine_dgrad:
+            assert x.grad.is_contiguous()
     p = {kk: v.detach() for kk, v in mod.named_parameters()}
     conv = dict(stride=base.stride, padding=base.padding, dilation=base.dilation, groups=1)
-    oy, odx, og = O_.layer_forward_backward(oalgo, x.detach(), base.weight, base.bias, p, cfg, dy, conv, torch.bfloat16)
+    oy, odx, og = O_.layer_forward_backward(oalgo, x.detach().to(torch.bfloat16), base.weight, base.bias, p, cfg, dy,
+                                            conv, torch.bfloat16)
     assert float((y.detach().float() - oy.float()).abs().max()) <= Y_REL * float(oy.float().abs().max())
     assert float((x.grad.float() - odx.float()).abs().max()) <= Y_REL * float(odx.float().abs().max())
     for kk, g in og.items():
@@ -400,5 +414,51 @@ def test_engine_option_variants_match_reference_fixtures(regime):
         case = cases[name]
         before = _lib.launch_count()
         y, dx, grads = _run_engine(case, regime)
-        assert _lib.launch_count() > before, name
+        if "/linear" in name:  # the 8-channel fixture conv has no TMA-legal layout; its contractions are cuDNN's
+            assert _lib.launch_count() > before, name
         _check(name, y, dx, grads, case["y"], case["dx"], case["grads"])
+
+
+def test_conv_engine_with_channel_sliced_gradient_and_input():
+    """Non-dense NHWC-looking tensors (channel slices of a concatenation — what torch.cat's backward hands to the
+    upsampler convolution of a UNet) must be densified, not passed through: regression test for a layout pass that
+    trusted Tensor.to(memory_format=channels_last) to copy."""
+    import torch.nn as nn
+
+    import lycoris_b200 as L
+
+    torch.manual_seed(3)
+    base = nn.Conv2d(64, 64, 3, 1, 1).cuda().to(torch.bfloat16)
+    for p in base.parameters():
+        p.requires_grad_(False)
+    mod = L.LokrModule("c", base, 1.0, 100000, 1, factor=8).cuda()
+    with torch.no_grad():
+        mod.lokr_w2.normal_(0, 0.02)
+    big = torch.randn(2, 96, 16, 16, device="cuda").contiguous(memory_format=torch.channels_last)
+    big.requires_grad_(True)
+    skip = torch.randn(2, 32, 16, 16, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+
+    def run():
+        big.grad = None
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = base(big[:, 16:80])                 # non-dense input: channel slice of an NHWC tensor
+            z = torch.cat([y, skip], dim=1)         # its gradient comes back as a channel slice, too
+        (z.float() * torch.linspace(-1, 1, z.numel(), device="cuda").view_as(z)).sum().backward()
+        return y.detach().float(), big.grad.detach().clone(), None if mod.lokr_w2.grad is None else mod.lokr_w2.grad.clone()
+
+    ref_w = (base.weight.float() + mod.get_weight(base.weight.shape).float() * mod.multiplier).to(torch.bfloat16)
+    plain = nn.Conv2d(64, 64, 3, 1, 1).cuda().to(torch.bfloat16)
+    with torch.no_grad():
+        plain.weight.copy_(ref_w)
+        plain.bias.copy_(base.bias)
+    mod.apply_to()
+    y, dx, gw = run()
+    mod.restore()
+    big.grad = None
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y2 = plain(big[:, 16:80])
+        z2 = torch.cat([y2, skip], dim=1)
+    (z2.float() * torch.linspace(-1, 1, z2.numel(), device="cuda").view_as(z2)).sum().backward()
+    assert rel_err(y, y2.detach().float()) <= 1e-2
+    assert rel_err(dx, big.grad) <= 2e-2, rel_err(dx, big.grad)
+    assert gw is not None and float(gw.abs().sum()) > 0
