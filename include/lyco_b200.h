@@ -32,7 +32,8 @@ extern "C" {
 
 /* element types */
 enum { LYCO_BF16 = 0, LYCO_F16 = 1, LYCO_F32 = 2 };
-enum { LYCO_NHWC = 0, LYCO_NCHW = 1 }; /* activation layouts of the convolution output */
+enum { LYCO_NHWC = 0, LYCO_NCHW = 1, LYCO_NCHW_F32 = 2 }; /* layout (and fp32 variant) of the convolution output */
+enum { LYCO_FILTER_FPROP = 0, LYCO_FILTER_DGRAD = 1, LYCO_FILTER_WBACK = 2 };
 
 /* adapter algorithms — lycoris/wrapper.py:45-55 network_module_dict keys */
 enum {
@@ -112,6 +113,21 @@ int lyco_conv2d_fprop(const void* X, const void* Wk, void* Y, const void* bias, 
                       int stride, int dtype, int y_layout, void* stream);
 /*   y_layout: LYCO_NHWC, or LYCO_NCHW — the epilogue writes Y as [Nb, O, P, Q] (PyTorch's default
  *   layout, what F.conv2d returns for an NCHW input) with channel-major TMA stores; needs P*Q % 32 == 0. */
+
+/*   LYCO_NCHW_F32: as LYCO_NCHW with an fp32 Y — the input gradient of a layer whose input was fp32 under
+ *   autocast comes back in the input's dtype without a separate cast pass. */
+
+/*
+ * Filter re-layouts between PyTorch's [O, C, R, S] and the operand layouts of the convolution kernels
+ * (taps = R*S <= 9):
+ *   LYCO_FILTER_FPROP  W' [O][C][taps] (16-bit)     -> Wk [O][taps][C]              B operand of lyco_conv2d_fprop
+ *   LYCO_FILTER_DGRAD  W' [O][C][taps] (16-bit)     -> Wd [C][taps flipped][O]      B operand of the dgrad call
+ *   LYCO_FILTER_WBACK  dWk [O][taps][C] (fp32)      -> dW' [O][C][taps]             what lyco_factor_grads indexes
+ * Replaces the permute/flip copies a PyTorch host would make around those calls (no counterpart in the
+ * reference: cuDNN consumes [O,C,R,S] directly, F.conv2d at lycoris/modules/locon.py:317,331).
+ */
+int lyco_filter_relayout(const void* in, void* out, int O, int C, int taps, int mode, int dtype,
+                         void* stream);
 
 /*
  * dst[b][c][r] = cast(src[b][r][c]) for b < batch: the activation layout pass in front of the im2col

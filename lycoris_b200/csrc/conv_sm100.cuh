@@ -70,19 +70,16 @@ conv_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   gemm_setup<false>(full_bar, empty_bar, tfull_bar, tempty_bar, tmem_slot, stages, warp, lane);
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total = p.m_tiles * p.n_tiles * p.splits;
+  const int worker = blockIdx.x, workers = gridDim.x;
 
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
-    for (int w = blockIdx.x; w < total; w += gridDim.x) {
-      const int split = w % p.splits;
-      const int tile = w / p.splits;
-      const int n_idx = tile % p.n_tiles;
-      const int m_idx = tile / p.n_tiles;
-      const int kb0 = static_cast<int>(static_cast<int64_t>(split) * p.k_blocks / p.splits);
-      const int kb1 = static_cast<int>(static_cast<int64_t>(split + 1) * p.k_blocks / p.splits);
+    for (WorkIter it(p, worker, workers); it.next();) {
+      const int n_idx = it.tile % p.n_tiles;
+      const int m_idx = it.tile / p.n_tiles;
+      const int kb0 = it.kb0, kb1 = it.kb1;
       if (MODE == MODE_FPROP) {
         // base output pixel of this M tile -> (image, row, col) -> input-space pixel coordinate
         const int m0 = m_idx * GEMM_BLOCK_M;
@@ -132,10 +129,8 @@ conv_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int w = blockIdx.x; w < total; w += gridDim.x) {
-      const int split = w % p.splits;
-      const int kb0 = static_cast<int>(static_cast<int64_t>(split) * p.k_blocks / p.splits);
-      const int kb1 = static_cast<int>(static_cast<int64_t>(split + 1) * p.k_blocks / p.splits);
+    for (WorkIter it(p, worker, workers); it.next();) {
+      const int kb0 = it.kb0, kb1 = it.kb1;
       ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * 256;
@@ -157,10 +152,9 @@ conv_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     int buf = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int w = blockIdx.x; w < total; w += gridDim.x) {
-      const int tile = w / p.splits;
-      const int n_idx = tile % p.n_tiles;
-      const int m_idx = tile / p.n_tiles;
+    for (WorkIter it(p, worker, workers); it.next();) {
+      const int n_idx = it.tile % p.n_tiles;
+      const int m_idx = it.tile / p.n_tiles;
       int col_base, col_limit;
       if (MODE == MODE_FPROP) {
         col_base = n_idx * block_n;

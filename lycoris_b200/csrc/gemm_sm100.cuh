@@ -44,7 +44,7 @@ constexpr int GEMM_EPI_BYTES = 4 * 2 * 2048;   // 4 epilogue warps x 2 staging b
 constexpr int GEMM_TMEM_COLS = 512;            // two accumulator stages at columns 0 and 256
 constexpr int GEMM_SMEM_BYTES = GEMM_RING_BYTES + GEMM_EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
-enum { EPI_STORE16 = 0, EPI_STORE_F32 = 1, EPI_ATOMIC_F32 = 2, EPI_STORE16_NCHW = 3 };
+enum { EPI_STORE16 = 0, EPI_STORE_F32 = 1, EPI_ATOMIC_F32 = 2, EPI_STORE16_NCHW = 3, EPI_STORE_F32_NCHW = 4 };
 __host__ __device__ constexpr bool epi_uses_tma(int epi) { return epi == EPI_STORE16 || epi == EPI_STORE16_NCHW; }
 
 struct GemmParams {
@@ -138,6 +138,23 @@ __device__ __forceinline__ void store_chunk_f32(const uint32_t (&r)[32], int row
   }
 }
 
+// fp32 NCHW epilogue (the input gradient of a convolution whose input was fp32 under autocast): lane = pixel, so
+// for each channel the warp writes 32 consecutive floats — one full 128-byte line per store, no staging needed.
+__device__ __forceinline__ void store_chunk_f32_nchw(const uint32_t (&r)[32], int row0, int col0, const GemmParams& p,
+                                                     int n_limit, int lane) {
+  if (col0 >= n_limit || row0 >= p.M) return;
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  add_bias32(v, p, col0, n_limit);
+  const int img = row0 / p.epi_pq;
+  float* base = reinterpret_cast<float*>(p.C) +
+                (static_cast<int64_t>(img) * p.N + col0) * p.epi_pq + (row0 - img * p.epi_pq) + lane;
+#pragma unroll
+  for (int j = 0; j < 32; ++j)
+    if (col0 + j < n_limit) base[static_cast<int64_t>(j) * p.epi_pq] = v[j];
+}
+
 // 16-bit epilogue for one 32-column chunk of this warp's 32 rows: registers -> SWIZZLE_64B staging
 // tile (32 rows x 64 B) -> one TMA store (full 64-byte row segments, asynchronous, clipped at M / N).
 // `stage` is this warp's pair of 2 KiB buffers; at most one store is left in flight when a buffer is reused.
@@ -204,6 +221,28 @@ __device__ __forceinline__ void store_chunk_tma_nchw(const uint32_t (&r)[32], in
   }
   buf ^= 1;
 }
+
+// Work distribution, identical in the three roles of a CTA (pair): units are (tile, reduction split) pairs handed
+// out round-robin, splits of one tile on neighbouring workers, n fastest across tiles (neighbours share A rows in
+// L2).  Every unit of a launch has the same number of k-blocks (+-1), which keeps the fp32-atomic epilogue of one
+// unit hidden behind the main loop of the next (a flattened equal-range scheduler with ragged units was measured
+// 5-10 % slower on the wgrad shapes: short units expose their epilogue).
+struct WorkIter {
+  int tile, kb0, kb1;  // current unit
+  int w, step, total, splits, k_blocks;
+  __device__ __forceinline__ WorkIter(const GemmParams& p, int worker, int workers)
+      : tile(0), kb0(0), kb1(0), w(worker), step(workers), total(p.m_tiles * p.n_tiles * p.splits), splits(p.splits),
+        k_blocks(p.k_blocks) {}
+  __device__ __forceinline__ bool next() {
+    if (w >= total) return false;
+    const int split = w % splits;
+    tile = w / splits;
+    kb0 = static_cast<int>(static_cast<int64_t>(split) * k_blocks / splits);
+    kb1 = static_cast<int>(static_cast<int64_t>(split + 1) * k_blocks / splits);
+    w += step;
+    return true;
+  }
+};
 
 template <bool PAIR>
 __device__ __forceinline__ void gemm_setup(uint64_t* full_bar, uint64_t* empty_bar, uint64_t* tfull_bar,
@@ -284,6 +323,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(uint32_t t_row, int row0, int
     const int col0 = col_base + c * 32;
     if (EPI == EPI_STORE16) store_chunk_tma(r, row0, col0, p, n_limit, tmap_c, stage, buf, lane);
     else if (EPI == EPI_STORE16_NCHW) store_chunk_tma_nchw(r, row0, col0, p, n_limit, tmap_c, stage, buf, lane);
+    else if (EPI == EPI_STORE_F32_NCHW) store_chunk_f32_nchw(r, row0, col0, p, n_limit, lane);
     else store_chunk_f32<EPI>(r, row0 + lane, col0, p, n_limit);
   }
 }
@@ -321,19 +361,15 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 
   const int workers = PAIR ? (gridDim.x >> 1) : gridDim.x;
   const int worker = PAIR ? (blockIdx.x >> 1) : blockIdx.x;
-  const int total = p.m_tiles * p.n_tiles * p.splits;
 
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
-    for (int w = worker; w < total; w += workers) {
-      const int split = w % p.splits;
-      const int tile = w / p.splits;
-      const int n_idx = tile % p.n_tiles;
-      const int m_idx = tile / p.n_tiles;
-      const int kb0 = static_cast<int>(static_cast<int64_t>(split) * p.k_blocks / p.splits);
-      const int kb1 = static_cast<int>(static_cast<int64_t>(split + 1) * p.k_blocks / p.splits);
+    for (WorkIter it(p, worker, workers); it.next();) {
+      const int n_idx = it.tile % p.n_tiles;
+      const int m_idx = it.tile / p.n_tiles;
+      const int kb0 = it.kb0, kb1 = it.kb1;
       const int m0 = m_idx * rows_per_tile + static_cast<int>(rank) * GEMM_BLOCK_M;
       const int n0 = n_idx * block_n + static_cast<int>(rank) * b_rows;
       for (int kb = kb0; kb < kb1; ++kb) {
@@ -382,10 +418,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int w = worker; w < total; w += workers) {
-      const int split = w % p.splits;
-      const int kb0 = static_cast<int>(static_cast<int64_t>(split) * p.k_blocks / p.splits);
-      const int kb1 = static_cast<int>(static_cast<int64_t>(split + 1) * p.k_blocks / p.splits);
+    for (WorkIter it(p, worker, workers); it.next();) {
+      const int kb0 = it.kb0, kb1 = it.kb1;
       ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * 256;
@@ -408,10 +442,9 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     int buf = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int w = worker; w < total; w += workers) {
-      const int tile = w / p.splits;
-      const int n_idx = tile % p.n_tiles;
-      const int m_idx = tile / p.n_tiles;
+    for (WorkIter it(p, worker, workers); it.next();) {
+      const int n_idx = it.tile % p.n_tiles;
+      const int m_idx = it.tile / p.n_tiles;
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tc_fence_after();
       const int row0 = m_idx * rows_per_tile + static_cast<int>(rank) * GEMM_BLOCK_M + ew * 32;

@@ -75,4 +75,70 @@ transpose_cast_kernel(const SRC* __restrict__ src, uint16_t* __restrict__ dst, i
   }
 }
 
+// Filter re-layouts around the implicit-GEMM convolutions (T = R*S taps, small).  All three read and write runs of
+// >= 64 contiguous bytes through a shared-memory tile.
+//   FILTER_FPROP : W' [O][C][T]  (PyTorch's [O,C,R,S])  -> Wk [O][T][C]        the fprop B operand
+//   FILTER_DGRAD : W' [O][C][T]                          -> Wd [C][T'][O], T' = T-1-t   flipped + transposed, the
+//                                                           B operand of dgrad-as-fprop
+//   FILTER_WBACK : dWk [O][T][C] fp32 (wgrad output)     -> dW' [O][C][T] fp32  (the layout the factor-gradient
+//                                                           kernels index)
+enum { FILTER_FPROP = 0, FILTER_DGRAD = 1, FILTER_WBACK = 2 };
+constexpr int FR_CCHUNK = 128;   // channels per block for the per-output-channel modes
+constexpr int FR_MAX_T = 25;     // up to 5x5 filters
+
+// FILTER_FPROP / FILTER_WBACK: grid = (ceil(C / FR_CCHUNK), O), block = 256
+template <typename T, bool BACK>
+__global__ void __launch_bounds__(256) filter_row_relayout_kernel(const T* __restrict__ in, T* __restrict__ out,
+                                                                   int C, int taps) {
+  extern __shared__ uint8_t fr_smem[];
+  T* tile = reinterpret_cast<T*>(fr_smem);  // [cn][taps + 1] (padded)
+  const int o = blockIdx.y, c0 = blockIdx.x * FR_CCHUNK;
+  const int cn = min(FR_CCHUNK, C - c0);
+  const int pitch = taps + 1;
+  const size_t row = static_cast<size_t>(o) * C * taps;
+  const int n = cn * taps;
+  if (!BACK) {
+    // in: [c][t] contiguous from (c0, 0); out: [t][c]
+    const T* src = in + row + static_cast<size_t>(c0) * taps;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) tile[(i / taps) * pitch + (i % taps)] = src[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int t = i / cn, c = i - t * cn;
+      out[row + static_cast<size_t>(t) * C + c0 + c] = tile[c * pitch + t];
+    }
+  } else {
+    // in: [t][c]; out: [c][t] contiguous from (c0, 0)
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int t = i / cn, c = i - t * cn;
+      tile[c * pitch + t] = in[row + static_cast<size_t>(t) * C + c0 + c];
+    }
+    __syncthreads();
+    T* dst = out + row + static_cast<size_t>(c0) * taps;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = tile[(i / taps) * pitch + (i % taps)];
+  }
+}
+
+// FILTER_DGRAD: grid = (ceil(C / 32), ceil(O / 32)), block = 256; tile [32 o][32 c * taps]
+__global__ void __launch_bounds__(256) filter_dgrad_relayout_kernel(const uint16_t* __restrict__ in,
+                                                                     uint16_t* __restrict__ out, int O, int C,
+                                                                     int taps) {
+  extern __shared__ uint8_t fr_smem[];
+  uint16_t* tile = reinterpret_cast<uint16_t*>(fr_smem);  // [32][32 * taps + 2]
+  const int o0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int on = min(32, O - o0), cn = min(32, C - c0);
+  const int run = cn * taps, pitch = 32 * taps + 2;
+  for (int i = threadIdx.x; i < on * run; i += blockDim.x) {
+    const int oo = i / run, k = i - oo * run;
+    tile[oo * pitch + k] = in[(static_cast<size_t>(o0 + oo) * C + c0) * taps + k];
+  }
+  __syncthreads();
+  // out[c][t'][o]: for fixed (c, t') the 32 output channels are contiguous
+  for (int i = threadIdx.x; i < cn * taps * 32; i += blockDim.x) {
+    const int oo = i & 31, ct = i >> 5;
+    const int c = ct / taps, tp = ct - c * taps;
+    if (oo < on)
+      out[(static_cast<size_t>(c0 + c) * taps + tp) * O + o0 + oo] = tile[oo * pitch + c * taps + (taps - 1 - tp)];
+  }
+}
+
 }  // namespace lyco

@@ -433,13 +433,10 @@ int lyco_gemm(const void* A, int a_mn_major, int64_t lda, const void* B, int b_m
     }
   }
   const long total = static_cast<long>(m_tiles) * n_tiles * splits;
-  if (tc.pair) {
-    const long slots = di.sms / 2;
-    const int grid = 2 * static_cast<int>(total < slots ? total : slots);
-    return dispatch_gemm<true>(a_mn, b_mn, epi, ta, tb, tcm, p, grid, stream);
-  }
-  const int grid = static_cast<int>(total < di.sms ? total : di.sms);
-  return dispatch_gemm<false>(a_mn, b_mn, epi, ta, tb, tcm, p, grid, stream);
+  const long slots = tc.pair ? di.sms / 2 : di.sms;
+  const int workers = static_cast<int>(total < slots ? total : slots);
+  if (tc.pair) return dispatch_gemm<true>(a_mn, b_mn, epi, ta, tb, tcm, p, 2 * workers, stream);
+  return dispatch_gemm<false>(a_mn, b_mn, epi, ta, tb, tcm, p, workers, stream);
 }
 
 int lyco_conv2d_fprop(const void* X, const void* Wk, void* Y, const void* bias, int bias_dtype, int Nb, int H,
@@ -447,7 +444,8 @@ int lyco_conv2d_fprop(const void* X, const void* Wk, void* Y, const void* bias, 
                       int y_layout, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!X || !Wk || !Y) return fail("lyco_conv2d_fprop: null operand");
-  if (y_layout != LYCO_NHWC && y_layout != LYCO_NCHW) return fail("lyco_conv2d_fprop: bad y_layout %d", y_layout);
+  if (y_layout != LYCO_NHWC && y_layout != LYCO_NCHW && y_layout != LYCO_NCHW_F32)
+    return fail("lyco_conv2d_fprop: bad y_layout %d", y_layout);
   if (dtype != LYCO_BF16 && dtype != LYCO_F16) return fail("lyco_conv2d_fprop: operands must be bf16/f16");
   if (C % 64 || O % 8) return fail("lyco_conv2d_fprop: needs C %% 64 == 0 and O %% 8 == 0 (C=%d O=%d)", C, O);
   if (stride < 1 || stride > 8 || R < 1 || S < 1) return fail("lyco_conv2d_fprop: bad geometry");
@@ -477,9 +475,12 @@ int lyco_conv2d_fprop(const void* X, const void* Wk, void* Y, const void* bias, 
   CUtensorMap ta, tb, tcm;
   if (make_tmap_im2col(&ta, X, Nb, H, W, C, R, S, pad_h, pad_w, stride, 128)) return 1;
   if (make_tmap(&tb, Wk, K, O, K, 64, bn)) return 1;
+  if (y_layout != LYCO_NHWC && (P * Q) % 32)
+    return fail("lyco_conv2d_fprop: NCHW output needs P*Q %% 32 == 0 (P*Q=%d)", P * Q);
   if (y_layout == LYCO_NCHW) {
-    if ((P * Q) % 32) return fail("lyco_conv2d_fprop: NCHW output needs P*Q %% 32 == 0 (P*Q=%d)", P * Q);
     if (make_tmap_c_nchw(&tcm, Y, static_cast<uint64_t>(P) * Q, O, Nb)) return 1;
+  } else if (y_layout == LYCO_NCHW_F32) {
+    memset(&tcm, 0, sizeof(tcm));  // written with plain coalesced stores
   } else if (make_tmap_c(&tcm, Y, O, M, O)) return 1;
   lyco::ConvParams cp;
   cp.g.epi_pq = P * Q;
@@ -492,7 +493,41 @@ int lyco_conv2d_fprop(const void* X, const void* Wk, void* Y, const void* bias, 
   const long total = static_cast<long>(cp.g.m_tiles) * cp.g.n_tiles;
   const int grid = static_cast<int>(total < di.sms ? total : di.sms);
   if (y_layout == LYCO_NCHW) return launch_conv<lyco::MODE_FPROP, lyco::EPI_STORE16_NCHW>(ta, tb, tcm, cp, grid, stream);
+  if (y_layout == LYCO_NCHW_F32)
+    return launch_conv<lyco::MODE_FPROP, lyco::EPI_STORE_F32_NCHW>(ta, tb, tcm, cp, grid, stream);
   return launch_conv<lyco::MODE_FPROP, lyco::EPI_STORE16>(ta, tb, tcm, cp, grid, stream);
+}
+
+int lyco_filter_relayout(const void* in, void* out, int O, int C, int taps, int mode, int dtype, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!in || !out) return fail("lyco_filter_relayout: null operand");
+  if (O < 1 || C < 1 || taps < 1 || taps > 9) return fail("lyco_filter_relayout: needs 1 <= R*S <= 9 (got %d)", taps);
+  if (O > 65535 * 32) return fail("lyco_filter_relayout: too many output channels");
+  DeviceInfo di;
+  if (device_info(&di)) return 1;
+  if (mode == LYCO_FILTER_WBACK) {
+    if (dtype != LYCO_F32) return fail("lyco_filter_relayout: the weight-gradient re-layout is fp32");
+    if (O > 65535) return fail("lyco_filter_relayout: too many output channels");
+    const dim3 grid(cdiv(C, lyco::FR_CCHUNK), O);
+    lyco::filter_row_relayout_kernel<float, true><<<grid, 256, lyco::FR_CCHUNK * (taps + 1) * 4, stream>>>(
+        static_cast<const float*>(in), static_cast<float*>(out), C, taps);
+  } else if (mode == LYCO_FILTER_FPROP) {
+    if (dtype != LYCO_BF16 && dtype != LYCO_F16) return fail("lyco_filter_relayout: filters are bf16/f16");
+    if (O > 65535) return fail("lyco_filter_relayout: too many output channels");
+    const dim3 grid(cdiv(C, lyco::FR_CCHUNK), O);
+    lyco::filter_row_relayout_kernel<uint16_t, false><<<grid, 256, lyco::FR_CCHUNK * (taps + 1) * 2, stream>>>(
+        static_cast<const uint16_t*>(in), static_cast<uint16_t*>(out), C, taps);
+  } else if (mode == LYCO_FILTER_DGRAD) {
+    if (dtype != LYCO_BF16 && dtype != LYCO_F16) return fail("lyco_filter_relayout: filters are bf16/f16");
+    const dim3 grid(cdiv(C, 32), cdiv(O, 32));
+    lyco::filter_dgrad_relayout_kernel<<<grid, 256, 32 * (32 * taps + 2) * 2, stream>>>(
+        static_cast<const uint16_t*>(in), static_cast<uint16_t*>(out), O, C, taps);
+  } else {
+    return fail("lyco_filter_relayout: bad mode %d", mode);
+  }
+  LYCO_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
 }
 
 int lyco_transpose_cast(const void* src, void* dst, int batch, int rows, int cols, int src_dtype, int dst_dtype,

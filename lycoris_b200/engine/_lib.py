@@ -27,6 +27,7 @@ EXPORTED_SYMBOLS = (
     "lyco_conv2d_fprop",
     "lyco_conv2d_wgrad",
     "lyco_transpose_cast",
+    "lyco_filter_relayout",
     "lyco_merge_weight",
     "lyco_factor_grads",
     "lyco_grad_prep",
@@ -93,6 +94,8 @@ def _bind(lib):
         c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,  # Nb H W C O R S pad_h pad_w stride
         c_int, c_int, c_void_p,  # dtype y_layout stream
     ]
+    lib.lyco_filter_relayout.restype = c_int
+    lib.lyco_filter_relayout.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
     lib.lyco_transpose_cast.restype = c_int
     lib.lyco_transpose_cast.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
     lib.lyco_conv2d_wgrad.restype = c_int

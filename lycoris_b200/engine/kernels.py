@@ -139,10 +139,43 @@ def as_nhwc(x, dtype=None):
     return out.copy_(x)
 
 
-def conv2d_fprop(x, wk, bias, R, S, pad, stride, out_nchw=False):
+FILTER_FPROP, FILTER_DGRAD, FILTER_WBACK = 0, 1, 2
+
+
+def filter_relayout(w, mode):
+    """Filter re-layouts on the engine (lyco_filter_relayout).  ``w``: [O, C, R, S] contiguous 16-bit for
+    FILTER_FPROP -> [O, R*S*C] and FILTER_DGRAD -> [C, R*S*O] (flipped taps); fp32 [O, R*S*C] with the 4-D shape
+    passed as ``w = (tensor, (O, C, R, S))`` for FILTER_WBACK -> [O, C, R, S].  Filters larger than 3x3 taps go
+    through PyTorch permutes."""
+    if mode == FILTER_WBACK:
+        t, (O, C, R, S) = w
+    else:
+        t = w
+        O, C, R, S = w.shape
+    taps = R * S
+    _require_cuda(t)
+    if taps > 9 or not t.is_contiguous() or O > 65535:
+        if mode == FILTER_FPROP:
+            return t.permute(0, 2, 3, 1).reshape(O, taps * C)
+        if mode == FILTER_DGRAD:
+            return t.flip(2, 3).permute(1, 2, 3, 0).reshape(C, taps * O)
+        return t.view(O, R, S, C).permute(0, 3, 1, 2).contiguous()
+    if mode == FILTER_FPROP:
+        out = torch.empty((O, taps * C), device=t.device, dtype=t.dtype)
+    elif mode == FILTER_DGRAD:
+        out = torch.empty((C, taps * O), device=t.device, dtype=t.dtype)
+    else:
+        out = torch.empty((O, C, R, S), device=t.device, dtype=t.dtype)
+    rc = _lib.load().lyco_filter_relayout(_ptr(t), _ptr(out), O, C, taps, mode, dtype_code(t.dtype), _stream())
+    _lib.check(rc, "filter_relayout")
+    return out
+
+
+def conv2d_fprop(x, wk, bias, R, S, pad, stride, out_nchw=False, out_dtype=None):
     """``x``: [Nb, C, H, W] in channels_last storage; ``wk``: [O, R*S*C] (filter as [O,R,S,C]).
     Returns y [Nb, O, P, Q]: channels_last storage, or plain contiguous NCHW with ``out_nchw`` (written
-    channel-major by the epilogue; needs P*Q % 32 == 0, otherwise the NHWC result is returned)."""
+    channel-major by the epilogue; needs P*Q % 32 == 0, otherwise the NHWC result is returned); with
+    ``out_dtype=torch.float32`` the NCHW result is written in fp32 (other layouts come back 16-bit)."""
     _require_cuda(x, wk, bias)
     x = as_nhwc(x)
     Nb, C, H, W = x.shape
@@ -150,13 +183,17 @@ def conv2d_fprop(x, wk, bias, R, S, pad, stride, out_nchw=False):
     P = (H + 2 * pad[0] - R) // stride + 1
     Q = (W + 2 * pad[1] - S) // stride + 1
     nchw = bool(out_nchw) and _NCHW_EPILOGUE and (P * Q) % 32 == 0
+    layout = 0
     if nchw:
-        y = torch.empty((Nb, O, P, Q), device=x.device, dtype=x.dtype)
+        # fp32 output only exists for the NCHW epilogue (plain coalesced stores); otherwise the caller casts
+        f32 = out_dtype == torch.float32
+        y = torch.empty((Nb, O, P, Q), device=x.device, dtype=torch.float32 if f32 else x.dtype)
+        layout = 2 if f32 else 1
     else:
         y = torch.empty((Nb, O, P, Q), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
     rc = _lib.load().lyco_conv2d_fprop(
         _ptr(x), _ptr(wk), _ptr(y), _ptr(bias), dtype_code(bias.dtype) if bias is not None else 0,
-        Nb, H, W, C, O, R, S, pad[0], pad[1], stride, dtype_code(x.dtype), 1 if nchw else 0, _stream())
+        Nb, H, W, C, O, R, S, pad[0], pad[1], stride, dtype_code(x.dtype), layout, _stream())
     _lib.check(rc, "conv2d_fprop")
     return y
 

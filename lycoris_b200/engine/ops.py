@@ -164,7 +164,7 @@ def _conv_forward(x, w, bias, cp):
         O, C, R, S = w.shape
         nchw_in = not x.is_contiguous(memory_format=torch.channels_last)
         xs = K.as_nhwc(x, w.dtype)
-        wk = w.permute(0, 2, 3, 1).reshape(O, R * S * C)  # filter taps outermost, channels contiguous
+        wk = K.filter_relayout(w.contiguous(), K.FILTER_FPROP)  # [O, R*S*C]: taps outermost, channels contiguous
         y = K.conv2d_fprop(xs, wk, bias, R, S, cp["padding"], cp["stride"][0], out_nchw=nchw_in)
         return y, xs, (True, nchw_in, x.dtype)
     xd = x.dtype
@@ -187,15 +187,16 @@ def _conv_backward(dy, x, w, cp, info, need_x, need_w):
         if need_x:
             if st == 1 and O % 64 == 0 and C % 8 == 0 and pad[0] <= R - 1 and pad[1] <= S - 1:
                 # input gradient = the same implicit GEMM over dY with the flipped, transposed filter
-                wd = w.flip(2, 3).permute(1, 2, 3, 0).reshape(C, R * S * O)
-                dx = K.conv2d_fprop(dyc, wd, None, R, S, (R - 1 - pad[0], S - 1 - pad[1]), 1, out_nchw=nchw_in)
+                wd = K.filter_relayout(w.contiguous(), K.FILTER_DGRAD)  # [C, R*S*O], taps flipped
+                dx = K.conv2d_fprop(dyc, wd, None, R, S, (R - 1 - pad[0], S - 1 - pad[1]), 1, out_nchw=nchw_in,
+                                    out_dtype=x_dtype)
             else:
                 dx = torch.ops.aten.convolution_backward(
                     dyc, x, w, None, cp["stride"], cp["padding"], cp["dilation"], False, [0, 0], cp["groups"],
                     [True, False, False])[0]
         if need_w:
             dwk = K.conv2d_wgrad(x, dyc, R, S, pad, st)  # [O, R*S*C] fp32
-            dw = dwk.view(O, R, S, C).permute(0, 3, 1, 2).contiguous()
+            dw = K.filter_relayout((dwk, (O, C, R, S)), K.FILTER_WBACK)
     else:
         dx, dw, _ = torch.ops.aten.convolution_backward(
             dy.contiguous(), x, w, None, cp["stride"], cp["padding"], cp["dilation"], False,

@@ -188,6 +188,28 @@ def test_conv_fprop_nchw_epilogue_equals_nhwc(Nb, C, O, H, W, stride):
     b = K.conv2d_fprop(x, wk, bias, 3, 3, (1, 1), stride, out_nchw=True)
     assert a.is_contiguous(memory_format=torch.channels_last) and b.is_contiguous()
     assert torch.equal(a.contiguous(), b)
+    c = K.conv2d_fprop(x, wk, bias, 3, 3, (1, 1), stride, out_nchw=True, out_dtype=torch.float32)
+    assert c.dtype == torch.float32 and c.is_contiguous()
+    assert torch.equal(c.to(torch.bfloat16), b)  # same accumulators, rounded once instead of not at all
     ref = torch.nn.functional.conv2d(x.float(), wk.view(O, 3, 3, C).permute(0, 3, 1, 2).float(), bias.float(),
                                      stride, 1)
     assert float((b.float() - ref).abs().max()) <= 2e-2 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("O,C,R,S", [(64, 64, 3, 3), (72, 200, 3, 3), (1280, 640, 3, 3), (128, 64, 1, 1), (40, 33, 2, 3)])
+def test_filter_relayouts_are_bit_exact(O, C, R, S):
+    """lyco_filter_relayout == the permute / flip copies it replaces, for all three modes."""
+    from lycoris_b200.engine import kernels as K
+
+    torch.manual_seed(O + C)
+    w = torch.randn(O, C, R, S, device="cuda").to(torch.bfloat16)
+    before = K._lib.launch_count()
+    wk = K.filter_relayout(w, K.FILTER_FPROP)
+    wd = K.filter_relayout(w, K.FILTER_DGRAD)
+    assert torch.equal(wk, w.permute(0, 2, 3, 1).reshape(O, R * S * C))
+    assert torch.equal(wd, w.flip(2, 3).permute(1, 2, 3, 0).reshape(C, R * S * O))
+    dwk = torch.randn(O, R * S * C, device="cuda")
+    dw = K.filter_relayout((dwk, (O, C, R, S)), K.FILTER_WBACK)
+    assert dw.shape == (O, C, R, S) and dw.is_contiguous()
+    assert torch.equal(dw, dwk.view(O, R, S, C).permute(0, 3, 1, 2).contiguous())
+    assert K._lib.launch_count() == before + 3
