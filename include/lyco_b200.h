@@ -208,7 +208,8 @@ int lyco_merge_weight(const lyco_delta_desc_t* d, const void* W, void* W_out,
 /*
  * Factor gradients from dW' (fp32 [N,K'], = dYᵀ·X of the merged contraction).
  * g0..g3 receive fp32 gradients with the shapes of f0..f3 (unused ones NULL);
- * they are zero-filled by the call.  `W` is needed by IA3 only.
+ * they are zero-filled by the call (one memset when the arrays lie back to back, each starting at the end of
+ * the previous one rounded up to 64 floats; otherwise one per array).  `W` is needed by IA3 only.
  * Replaces autograd through the chain listed at lyco_merge_weight, incl.
  * HadaWeight.backward lycoris/functional/loha.py:18-30 and torch.kron backward.
  */

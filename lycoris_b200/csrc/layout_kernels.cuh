@@ -86,58 +86,71 @@ enum { FILTER_FPROP = 0, FILTER_DGRAD = 1, FILTER_WBACK = 2 };
 constexpr int FR_CCHUNK = 128;   // channels per block for the per-output-channel modes
 constexpr int FR_MAX_T = 25;     // up to 5x5 filters
 
-// FILTER_FPROP / FILTER_WBACK: grid = (ceil(C / FR_CCHUNK), O), block = 256
+// FILTER_FPROP / FILTER_WBACK: grid = (ceil(C / FR_CCHUNK), O), block = 256.  All global traffic is 16-byte
+// vectors (C % 8 == 0 for 16-bit, C % 4 == 0 for fp32; 16-byte aligned bases); the transposition happens in the
+// shared-memory tile, kept in [c][t] order.
 template <typename T, bool BACK>
 __global__ void __launch_bounds__(256) filter_row_relayout_kernel(const T* __restrict__ in, T* __restrict__ out,
                                                                    int C, int taps) {
-  extern __shared__ uint8_t fr_smem[];
-  T* tile = reinterpret_cast<T*>(fr_smem);  // [cn][taps + 1] (padded)
+  constexpr int V = 16 / sizeof(T);
+  extern __shared__ uint4 fr_smem4[];
+  T* tile = reinterpret_cast<T*>(fr_smem4);  // [cn][taps]
   const int o = blockIdx.y, c0 = blockIdx.x * FR_CCHUNK;
   const int cn = min(FR_CCHUNK, C - c0);
-  const int pitch = taps + 1;
   const size_t row = static_cast<size_t>(o) * C * taps;
-  const int n = cn * taps;
+  const int nvec = cn * taps / V, groups = cn / V, items = groups * taps;
   if (!BACK) {
-    // in: [c][t] contiguous from (c0, 0); out: [t][c]
-    const T* src = in + row + static_cast<size_t>(c0) * taps;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) tile[(i / taps) * pitch + (i % taps)] = src[i];
+    const uint4* src = reinterpret_cast<const uint4*>(in + row + static_cast<size_t>(c0) * taps);
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) fr_smem4[i] = src[i];
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const int t = i / cn, c = i - t * cn;
-      out[row + static_cast<size_t>(t) * C + c0 + c] = tile[c * pitch + t];
+    for (int i = threadIdx.x; i < items; i += blockDim.x) {
+      const int t = i / groups, cg = i - t * groups;
+      T v[V];
+#pragma unroll
+      for (int j = 0; j < V; ++j) v[j] = tile[(cg * V + j) * taps + t];
+      *reinterpret_cast<uint4*>(out + row + static_cast<size_t>(t) * C + c0 + cg * V) = *reinterpret_cast<uint4*>(v);
     }
   } else {
-    // in: [t][c]; out: [c][t] contiguous from (c0, 0)
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const int t = i / cn, c = i - t * cn;
-      tile[c * pitch + t] = in[row + static_cast<size_t>(t) * C + c0 + c];
+    for (int i = threadIdx.x; i < items; i += blockDim.x) {
+      const int t = i / groups, cg = i - t * groups;
+      T v[V];
+      *reinterpret_cast<uint4*>(v) =
+          *reinterpret_cast<const uint4*>(in + row + static_cast<size_t>(t) * C + c0 + cg * V);
+#pragma unroll
+      for (int j = 0; j < V; ++j) tile[(cg * V + j) * taps + t] = v[j];
     }
     __syncthreads();
-    T* dst = out + row + static_cast<size_t>(c0) * taps;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = tile[(i / taps) * pitch + (i % taps)];
+    uint4* dst = reinterpret_cast<uint4*>(out + row + static_cast<size_t>(c0) * taps);
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) dst[i] = fr_smem4[i];
   }
 }
 
-// FILTER_DGRAD: grid = (ceil(C / 32), ceil(O / 32)), block = 256; tile [32 o][32 c * taps]
+// FILTER_DGRAD: grid = (ceil(C / 32), ceil(O / 32)), block = 256; tile [32 o][32 c * taps (+8 pad)], 16-byte
+// vectors on both sides (C % 8 == 0, O % 8 == 0).
 __global__ void __launch_bounds__(256) filter_dgrad_relayout_kernel(const uint16_t* __restrict__ in,
                                                                      uint16_t* __restrict__ out, int O, int C,
                                                                      int taps) {
-  extern __shared__ uint8_t fr_smem[];
-  uint16_t* tile = reinterpret_cast<uint16_t*>(fr_smem);  // [32][32 * taps + 2]
+  extern __shared__ uint4 fr_smem4[];
+  uint16_t* tile = reinterpret_cast<uint16_t*>(fr_smem4);
   const int o0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
   const int on = min(32, O - o0), cn = min(32, C - c0);
-  const int run = cn * taps, pitch = 32 * taps + 2;
-  for (int i = threadIdx.x; i < on * run; i += blockDim.x) {
-    const int oo = i / run, k = i - oo * run;
-    tile[oo * pitch + k] = in[(static_cast<size_t>(o0 + oo) * C + c0) * taps + k];
+  const int run = cn * taps, rvec = run / 8, pitch = 32 * taps + 8;
+  for (int i = threadIdx.x; i < on * rvec; i += blockDim.x) {
+    const int oo = i / rvec, k = i - oo * rvec;
+    reinterpret_cast<uint4*>(tile + oo * pitch)[k] =
+        reinterpret_cast<const uint4*>(in + (static_cast<size_t>(o0 + oo) * C + c0) * taps)[k];
   }
   __syncthreads();
-  // out[c][t'][o]: for fixed (c, t') the 32 output channels are contiguous
-  for (int i = threadIdx.x; i < cn * taps * 32; i += blockDim.x) {
-    const int oo = i & 31, ct = i >> 5;
+  // out[c][t'][o]: for fixed (c, t') the output channels are contiguous; 4 lanes write one 64-byte run
+  const int og = on / 8;
+  for (int i = threadIdx.x; i < run * og; i += blockDim.x) {
+    const int g = i % og, ct = i / og;
     const int c = ct / taps, tp = ct - c * taps;
-    if (oo < on)
-      out[(static_cast<size_t>(c0 + c) * taps + tp) * O + o0 + oo] = tile[oo * pitch + c * taps + (taps - 1 - tp)];
+    uint16_t v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = tile[(g * 8 + j) * pitch + c * taps + (taps - 1 - tp)];
+    *reinterpret_cast<uint4*>(out + (static_cast<size_t>(c0 + c) * taps + tp) * O + o0 + g * 8) =
+        *reinterpret_cast<uint4*>(v);
   }
 }
 

@@ -503,24 +503,27 @@ int lyco_filter_relayout(const void* in, void* out, int O, int C, int taps, int 
   if (!in || !out) return fail("lyco_filter_relayout: null operand");
   if (O < 1 || C < 1 || taps < 1 || taps > 9) return fail("lyco_filter_relayout: needs 1 <= R*S <= 9 (got %d)", taps);
   if (O > 65535 * 32) return fail("lyco_filter_relayout: too many output channels");
+  if (C % 8 || O % 8) return fail("lyco_filter_relayout: needs C %% 8 == 0 and O %% 8 == 0 (C=%d O=%d)", C, O);
+  if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15)
+    return fail("lyco_filter_relayout: arrays must be 16-byte aligned");
   DeviceInfo di;
   if (device_info(&di)) return 1;
   if (mode == LYCO_FILTER_WBACK) {
     if (dtype != LYCO_F32) return fail("lyco_filter_relayout: the weight-gradient re-layout is fp32");
     if (O > 65535) return fail("lyco_filter_relayout: too many output channels");
     const dim3 grid(cdiv(C, lyco::FR_CCHUNK), O);
-    lyco::filter_row_relayout_kernel<float, true><<<grid, 256, lyco::FR_CCHUNK * (taps + 1) * 4, stream>>>(
+    lyco::filter_row_relayout_kernel<float, true><<<grid, 256, lyco::FR_CCHUNK * taps * 4, stream>>>(
         static_cast<const float*>(in), static_cast<float*>(out), C, taps);
   } else if (mode == LYCO_FILTER_FPROP) {
     if (dtype != LYCO_BF16 && dtype != LYCO_F16) return fail("lyco_filter_relayout: filters are bf16/f16");
     if (O > 65535) return fail("lyco_filter_relayout: too many output channels");
     const dim3 grid(cdiv(C, lyco::FR_CCHUNK), O);
-    lyco::filter_row_relayout_kernel<uint16_t, false><<<grid, 256, lyco::FR_CCHUNK * (taps + 1) * 2, stream>>>(
+    lyco::filter_row_relayout_kernel<uint16_t, false><<<grid, 256, lyco::FR_CCHUNK * taps * 2, stream>>>(
         static_cast<const uint16_t*>(in), static_cast<uint16_t*>(out), C, taps);
   } else if (mode == LYCO_FILTER_DGRAD) {
     if (dtype != LYCO_BF16 && dtype != LYCO_F16) return fail("lyco_filter_relayout: filters are bf16/f16");
     const dim3 grid(cdiv(C, 32), cdiv(O, 32));
-    lyco::filter_dgrad_relayout_kernel<<<grid, 256, 32 * (32 * taps + 2) * 2, stream>>>(
+    lyco::filter_dgrad_relayout_kernel<<<grid, 256, 32 * (32 * taps + 8) * 2, stream>>>(
         static_cast<const uint16_t*>(in), static_cast<uint16_t*>(out), O, C, taps);
   } else {
     return fail("lyco_filter_relayout: bad mode %d", mode);
@@ -655,6 +658,19 @@ int lyco_merge_weight(const lyco_delta_desc_t* d, const void* W, void* W_out, vo
   return 0;
 }
 
+// Zero up to four gradient arrays: ONE memset when the caller laid them out back to back (each array starting at
+// the end of the previous one rounded up to 64 floats — what engine/kernels.py:factor_grads allocates), else one each.
+int zero_grads(float* const* g, const size_t* n, int count, cudaStream_t stream) {
+  bool packed = true;
+  for (int i = 1; i < count; ++i) packed = packed && g[i] == g[i - 1] + ((n[i - 1] + 63) / 64) * 64;
+  if (packed && count > 1) {
+    LYCO_CUDA(cudaMemsetAsync(g[0], 0, sizeof(float) * static_cast<size_t>(g[count - 1] + n[count - 1] - g[0]), stream));
+    return 0;
+  }
+  for (int i = 0; i < count; ++i) LYCO_CUDA(cudaMemsetAsync(g[i], 0, sizeof(float) * n[i], stream));
+  return 0;
+}
+
 int lyco_factor_grads(const lyco_delta_desc_t* d, const float* dW, const void* W, float* g0, float* g1,
                       float* g2, float* g3, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -669,12 +685,10 @@ int lyco_factor_grads(const lyco_delta_desc_t* d, const float* dW, const void* W
     case LYCO_ALGO_LOHA: {
       const bool loha = d->algo == LYCO_ALGO_LOHA;
       if (!g0 || !g1 || (loha && (!g2 || !g3))) return fail("lyco_factor_grads: missing gradient buffers");
-      LYCO_CUDA(cudaMemsetAsync(g0, 0, sizeof(float) * static_cast<size_t>(N) * r, stream));
-      LYCO_CUDA(cudaMemsetAsync(g1, 0, sizeof(float) * static_cast<size_t>(r) * K, stream));
-      if (loha) {
-        LYCO_CUDA(cudaMemsetAsync(g2, 0, sizeof(float) * static_cast<size_t>(N) * r, stream));
-        LYCO_CUDA(cudaMemsetAsync(g3, 0, sizeof(float) * static_cast<size_t>(r) * K, stream));
-      }
+      float* const gs[4] = {g0, g1, g2, g3};
+      const size_t ns[4] = {static_cast<size_t>(N) * r, static_cast<size_t>(r) * K, static_cast<size_t>(N) * r,
+                            static_cast<size_t>(r) * K};
+      if (zero_grads(gs, ns, loha ? 4 : 2, stream)) return 1;
       const int grid = cdiv(N, lyco::LR_ROWS) * cdiv(K, lyco::LR_COLS);
       if (loha) lyco::grad_lowrank_kernel<true><<<grid, 256, 0, stream>>>(*d, dW, g0, g1, g2, g3);
       else lyco::grad_lowrank_kernel<false><<<grid, 256, 0, stream>>>(*d, dW, g0, g1, g2, g3);
@@ -684,8 +698,9 @@ int lyco_factor_grads(const lyco_delta_desc_t* d, const float* dW, const void* W
       if (!g0 || !g1) return fail("lyco_factor_grads: missing gradient buffers");
       const size_t n_w1 = static_cast<size_t>(d->up) * d->uq;
       const int64_t plane = static_cast<int64_t>(d->vp) * d->vq;
-      LYCO_CUDA(cudaMemsetAsync(g0, 0, sizeof(float) * n_w1, stream));
-      LYCO_CUDA(cudaMemsetAsync(g1, 0, sizeof(float) * static_cast<size_t>(plane), stream));
+      float* const gs[2] = {g0, g1};
+      const size_t ns[2] = {n_w1, static_cast<size_t>(plane)};
+      if (zero_grads(gs, ns, 2, stream)) return 1;
       if (d->up > 65535) return fail("lyco_factor_grads: lokr up=%d too large", d->up);
       const bool vec4 = (d->vq % 4 == 0) && (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(dW) & 15) == 0);
       const size_t smem = sizeof(float) * static_cast<size_t>(d->uq);

@@ -154,7 +154,7 @@ def filter_relayout(w, mode):
         O, C, R, S = w.shape
     taps = R * S
     _require_cuda(t)
-    if taps > 9 or not t.is_contiguous() or O > 65535:
+    if taps > 9 or not t.is_contiguous() or O > 65535 or C % 8 or O % 8:
         if mode == FILTER_FPROP:
             return t.permute(0, 2, 3, 1).reshape(O, taps * C)
         if mode == FILTER_DGRAD:
@@ -253,7 +253,14 @@ def factor_grads(desc: DeltaDesc, dW: torch.Tensor, W, shapes):
     """fp32 gradients of the factor arrays from fp32 ``dW' = dYᵀ·X``."""
     _require_cuda(dW)
     assert dW.dtype == torch.float32 and dW.is_contiguous()
-    gs = [torch.empty(s, device=dW.device, dtype=torch.float32) for s in shapes]
+    # one buffer, arrays back to back at 64-float granularity: the library zero-fills them with ONE memset
+    sizes = [int(torch.Size(s).numel()) for s in shapes]
+    offs, total = [], 0
+    for n in sizes:
+        offs.append(total)
+        total += (n + 63) // 64 * 64
+    flat = torch.empty(total, device=dW.device, dtype=torch.float32)
+    gs = [flat[o:o + n].view(s) for o, n, s in zip(offs, sizes, shapes)]
     g = gs + [None] * (4 - len(gs))
     rc = _lib.load().lyco_factor_grads(
         ctypes.byref(desc), _ptr(dW), _ptr(W), _ptr(g[0]), _ptr(g[1]), _ptr(g[2]), _ptr(g[3]), _stream()

@@ -196,7 +196,7 @@ def test_conv_fprop_nchw_epilogue_equals_nhwc(Nb, C, O, H, W, stride):
     assert float((b.float() - ref).abs().max()) <= 2e-2 * float(ref.abs().max())
 
 
-@pytest.mark.parametrize("O,C,R,S", [(64, 64, 3, 3), (72, 200, 3, 3), (1280, 640, 3, 3), (128, 64, 1, 1), (40, 33, 2, 3)])
+@pytest.mark.parametrize("O,C,R,S", [(64, 64, 3, 3), (72, 200, 3, 3), (1280, 640, 3, 3), (128, 64, 1, 1), (40, 24, 2, 3), (320, 960, 3, 3)])
 def test_filter_relayouts_are_bit_exact(O, C, R, S):
     """lyco_filter_relayout == the permute / flip copies it replaces, for all three modes."""
     from lycoris_b200.engine import kernels as K
@@ -212,4 +212,4 @@ def test_filter_relayouts_are_bit_exact(O, C, R, S):
     dw = K.filter_relayout((dwk, (O, C, R, S)), K.FILTER_WBACK)
     assert dw.shape == (O, C, R, S) and dw.is_contiguous()
     assert torch.equal(dw, dwk.view(O, R, S, C).permute(0, 3, 1, 2).contiguous())
-    assert K._lib.launch_count() == before + 3
+    assert K._lib.launch_count() == before + 3  # all three ran on the engine
