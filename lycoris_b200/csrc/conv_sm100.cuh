@@ -38,7 +38,22 @@ __device__ __forceinline__ void tma_im2col_4d(void* smem_dst, const CUtensorMap*
       : "memory");
 }
 
-template <int MODE, int EPI>
+// Same gather issued by a member of a CTA pair: completion is signalled on the LEADER's mbarrier.
+__device__ __forceinline__ void tma_im2col_4d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr,
+                                                   int32_t c, int32_t w, int32_t h, int32_t n, uint16_t off_w,
+                                                   uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(ptx::smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w),
+      "h"(off_h)
+      : "memory");
+}
+
+// PAIR: a CTA pair (cta_group::2) computes a 256-row tile; each member gathers its own 128 rows of A and half of the
+// B columns, the leader issues the MMAs (same arrangement as gemm_sm100_kernel<true, ...>).
+template <bool PAIR, int MODE, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 conv_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const __grid_constant__ CUtensorMap tmap_c, const ConvParams cp) {
@@ -58,19 +73,23 @@ conv_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0;  // 0 = leader
   const int block_n = p.block_n;
-  const int stage_bytes = GEMM_A_BYTES + block_n * GEMM_BLOCK_K * 2;
+  const int b_cols = PAIR ? block_n / 2 : block_n;  // B columns (N) this CTA stages
+  const int stage_bytes = GEMM_A_BYTES + b_cols * GEMM_BLOCK_K * 2;
   const int stages = p.stages;
+  const int rows_per_tile = PAIR ? 2 * GEMM_BLOCK_M : GEMM_BLOCK_M;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_a);
     ptx::prefetch_tmap(&tmap_b);
     if (epi_uses_tma(EPI)) ptx::prefetch_tmap(&tmap_c);
   }
-  gemm_setup<false>(full_bar, empty_bar, tfull_bar, tempty_bar, tmem_slot, stages, warp, lane);
+  gemm_setup<PAIR>(full_bar, empty_bar, tfull_bar, tempty_bar, tmem_slot, stages, warp, lane);
   const uint32_t tmem_base = *tmem_slot;
 
-  const int worker = blockIdx.x, workers = gridDim.x;
+  const int workers = PAIR ? (gridDim.x >> 1) : gridDim.x;
+  const int worker = PAIR ? (blockIdx.x >> 1) : blockIdx.x;
 
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -81,8 +100,9 @@ conv_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const int m_idx = it.tile / p.n_tiles;
       const int kb0 = it.kb0, kb1 = it.kb1;
       if (MODE == MODE_FPROP) {
-        // base output pixel of this M tile -> (image, row, col) -> input-space pixel coordinate
-        const int m0 = m_idx * GEMM_BLOCK_M;
+        // base output pixel of this CTA's 128 rows -> (image, row, col) -> input-space pixel coordinate
+        const int m0 = m_idx * rows_per_tile + static_cast<int>(rank) * GEMM_BLOCK_M;
+        const int n0 = n_idx * block_n + static_cast<int>(rank) * b_cols;
         const int img = m0 / cp.PQ, rem = m0 - img * cp.PQ;
         const int py = rem / cp.Q, px = rem - py * cp.Q;
         const int w0 = px * cp.stride + cp.low_w, h0 = py * cp.stride + cp.low_h;
@@ -90,41 +110,60 @@ conv_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           const int tap = kb / cp.CB, cb = kb - tap * cp.CB;
           const int fr = tap / cp.S, fs = tap - fr * cp.S;
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          ptx::mbar_expect_tx(&full_bar[stage], stage_bytes);
           uint8_t* sa = smem + stage * stage_bytes;
           uint8_t* sb = sa + GEMM_A_BYTES;
-          tma_im2col_4d(sa, &tmap_a, &full_bar[stage], cb * 64, w0, h0, img, static_cast<uint16_t>(fs),
-                        static_cast<uint16_t>(fr));
-          ptx::tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * GEMM_BLOCK_K, n_idx * block_n);
+          if (PAIR) {
+            const uint32_t full_leader = ptx::mapa(ptx::smem_u32(&full_bar[stage]), 0);
+            ptx::mbar_expect_tx_cluster(full_leader, stage_bytes);
+            tma_im2col_4d_pair(sa, &tmap_a, full_leader, cb * 64, w0, h0, img, static_cast<uint16_t>(fs),
+                               static_cast<uint16_t>(fr));
+            ptx::tma_load_2d_pair(sb, &tmap_b, full_leader, kb * GEMM_BLOCK_K, n0);
+          } else {
+            ptx::mbar_expect_tx(&full_bar[stage], stage_bytes);
+            tma_im2col_4d(sa, &tmap_a, &full_bar[stage], cb * 64, w0, h0, img, static_cast<uint16_t>(fs),
+                          static_cast<uint16_t>(fr));
+            ptx::tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * GEMM_BLOCK_K, n0);
+          }
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       } else {
         const int tap = n_idx / cp.tiles_per_tap;
-        const int c0 = (n_idx - tap * cp.tiles_per_tap) * block_n;
+        const int c0 = (n_idx - tap * cp.tiles_per_tap) * block_n + static_cast<int>(rank) * b_cols;
         const int fr = tap / cp.S, fs = tap - fr * cp.S;
+        const int o0 = m_idx * rows_per_tile + static_cast<int>(rank) * GEMM_BLOCK_M;
         for (int kb = kb0; kb < kb1; ++kb) {
           const int m0 = kb * GEMM_BLOCK_K;  // first pixel of this reduction block
           const int img = m0 / cp.PQ, rem = m0 - img * cp.PQ;
           const int py = rem / cp.Q, px = rem - py * cp.Q;
           const int w0 = px * cp.stride + cp.low_w, h0 = py * cp.stride + cp.low_h;
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          ptx::mbar_expect_tx(&full_bar[stage], stage_bytes);
           uint8_t* sa = smem + stage * stage_bytes;
           uint8_t* sb = sa + GEMM_A_BYTES;
+          if (PAIR) {
+            const uint32_t full_leader = ptx::mapa(ptx::smem_u32(&full_bar[stage]), 0);
+            ptx::mbar_expect_tx_cluster(full_leader, stage_bytes);
 #pragma unroll
-          for (int j = 0; j < GEMM_BLOCK_M / 64; ++j)
-            ptx::tma_load_2d(sa + j * GEMM_ATOM_BYTES, &tmap_a, &full_bar[stage], m_idx * GEMM_BLOCK_M + j * 64,
-                             kb * GEMM_BLOCK_K);
-          for (int j = 0; j < block_n / 64; ++j)
-            tma_im2col_4d(sb + j * GEMM_ATOM_BYTES, &tmap_b, &full_bar[stage], c0 + j * 64, w0, h0, img,
-                          static_cast<uint16_t>(fs), static_cast<uint16_t>(fr));
+            for (int j = 0; j < GEMM_BLOCK_M / 64; ++j)
+              ptx::tma_load_2d_pair(sa + j * GEMM_ATOM_BYTES, &tmap_a, full_leader, o0 + j * 64, kb * GEMM_BLOCK_K);
+            for (int j = 0; j < b_cols / 64; ++j)
+              tma_im2col_4d_pair(sb + j * GEMM_ATOM_BYTES, &tmap_b, full_leader, c0 + j * 64, w0, h0, img,
+                                 static_cast<uint16_t>(fs), static_cast<uint16_t>(fr));
+          } else {
+            ptx::mbar_expect_tx(&full_bar[stage], stage_bytes);
+#pragma unroll
+            for (int j = 0; j < GEMM_BLOCK_M / 64; ++j)
+              ptx::tma_load_2d(sa + j * GEMM_ATOM_BYTES, &tmap_a, &full_bar[stage], o0 + j * 64, kb * GEMM_BLOCK_K);
+            for (int j = 0; j < b_cols / 64; ++j)
+              tma_im2col_4d(sb + j * GEMM_ATOM_BYTES, &tmap_b, &full_bar[stage], c0 + j * 64, w0, h0, img,
+                            static_cast<uint16_t>(fs), static_cast<uint16_t>(fr));
+          }
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // -------------------------------------------------------------- MMA issuer
-    const uint32_t idesc = ptx::make_idesc_f16(p.fmt, GEMM_BLOCK_M, block_n, A_MN ? 1 : 0, B_MN ? 1 : 0);
+  } else if (warp == 1 && lane == 0 && rank == 0) {
+    // ------------------------------------------------- MMA issuer (leader CTA only for a pair)
+    const uint32_t idesc = ptx::make_idesc_f16(p.fmt, rows_per_tile, block_n, A_MN ? 1 : 0, B_MN ? 1 : 0);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -138,10 +177,11 @@ conv_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after();
         const uint32_t sa = ptx::smem_u32(smem + stage * stage_bytes);
-        gemm_issue_kblock<false, A_MN, B_MN>(sa, sa + GEMM_A_BYTES, d_tmem, idesc, kb == kb0, &empty_bar[stage]);
+        gemm_issue_kblock<PAIR, A_MN, B_MN>(sa, sa + GEMM_A_BYTES, d_tmem, idesc, kb == kb0, &empty_bar[stage]);
         if (++stage == stages) { stage = 0; phase ^= 1; }
       }
-      ptx::umma_commit(&tfull_bar[acc]);
+      if (PAIR) ptx::umma_commit_pair(&tfull_bar[acc], 0b11);
+      else ptx::umma_commit(&tfull_bar[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -166,17 +206,17 @@ conv_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tc_fence_after();
-      const int row0 = m_idx * GEMM_BLOCK_M + ew * 32;
+      const int row0 = m_idx * rows_per_tile + static_cast<int>(rank) * GEMM_BLOCK_M + ew * 32;
       const uint32_t t_row = tmem_base + acc * 256 + (static_cast<uint32_t>(ew * 32) << 16);
-      gemm_epilogue_tile<false, EPI>(t_row, row0, col_base, col_limit, block_n, p, &tmap_c, stage_buf, buf,
-                                     &tempty_bar[acc], lane);
+      gemm_epilogue_tile<PAIR, EPI>(t_row, row0, col_base, col_limit, block_n, p, &tmap_c, stage_buf, buf,
+                                    &tempty_bar[acc], lane);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
     if (epi_uses_tma(EPI) && lane == 0) ptx::tma_store_wait_read<0>();
   }
 
-  gemm_teardown<false>(tmem_base, warp);
+  gemm_teardown<PAIR>(tmem_base, warp);
 }
 
 }  // namespace lyco

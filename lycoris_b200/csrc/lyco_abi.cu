@@ -225,13 +225,27 @@ int dispatch_gemm(bool a_mn, bool b_mn, int epi, const CUtensorMap& ta, const CU
 #undef LYCO_EPI
 }
 
-template <int MODE, int EPI>
-int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const lyco::ConvParams& cp,
-                int grid, cudaStream_t stream) {
-  auto kern = lyco::conv_sm100_kernel<MODE, EPI>;
+template <bool PAIR, int MODE, int EPI>
+int launch_conv_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const lyco::ConvParams& cp,
+                  int grid, cudaStream_t stream) {
+  auto kern = lyco::conv_sm100_kernel<PAIR, MODE, EPI>;
   static bool configured[64] = {};
   if (ensure_smem(kern, configured)) return 1;
-  return launch_persistent(kern, false, ta, tb, tc, cp, grid, stream);
+  return launch_persistent(kern, PAIR, ta, tb, tc, cp, grid, stream);
+}
+
+// `workers` = CTAs (single) or CTA pairs (pair) to launch
+template <int MODE, int EPI>
+int launch_conv(bool pair, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+                const lyco::ConvParams& cp, int workers, cudaStream_t stream) {
+  if (pair) return launch_conv_t<true, MODE, EPI>(ta, tb, tc, cp, 2 * workers, stream);
+  return launch_conv_t<false, MODE, EPI>(ta, tb, tc, cp, workers, stream);
+}
+
+inline bool conv_pair_enabled() {
+  // LYCO_CONV_PAIR=0 keeps the convolutions on single-CTA tiles (A/B comparisons)
+  static const bool on = []() { const char* e = getenv("LYCO_CONV_PAIR"); return !(e && *e == '0'); }();
+  return on;
 }
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
@@ -459,22 +473,30 @@ int lyco_conv2d_fprop(const void* X, const void* Wk, void* Y, const void* bias, 
   if (M64 > (1ll << 30)) return fail("lyco_conv2d_fprop: too many output pixels");
   const int M = static_cast<int>(M64), K = R * S * C;
   TileChoice tc = pick_tile(M, O, di.sms, 1, false);
-  tc.pair = false;  // the im2col producer is single-CTA for now
   {
     double best = 1e30;
-    for (int bn = 256; bn >= 32; bn -= 32) {
-      if (bn > 32 && bn - 32 >= O) continue;
-      const long tiles = static_cast<long>(cdiv(M, 128)) * cdiv(O, bn);
-      const long waves = (tiles + di.sms - 1) / di.sms;
-      const double cost = waves * tile_cost(false, bn);
-      if (cost < best * 0.995) { best = cost; tc.bn = bn; }
+    for (int pair = 1; pair >= 0; --pair) {
+      if (pair && (M <= 128 || !conv_pair_enabled())) continue;
+      for (int bn = 256; bn >= 32; bn -= 32) {
+        if (!tile_valid(pair, bn, false)) continue;
+        if (bn > 32 && bn - 32 >= O) continue;
+        const long tiles = static_cast<long>(cdiv(M, pair ? 256 : 128)) * cdiv(O, bn);
+        const long slots = pair ? di.sms / 2 : di.sms;
+        const long waves = (tiles + slots - 1) / slots;
+        const double cost = waves * tile_cost(pair, bn);
+        if (cost < best * 0.995) { best = cost; tc.pair = pair != 0; tc.bn = bn; }
+      }
     }
   }
-  if (const char* e = getenv("LYCO_CONV_BN")) { const int f = atoi(e); if (f >= 32 && f <= 256 && f % 32 == 0) tc.bn = f; }
+  if (const char* e = getenv("LYCO_CONV_BN")) {
+    const int f = atoi(e);
+    if (tile_valid(tc.pair, f, false)) tc.bn = f;
+  }
   const int bn = tc.bn;
+  const bool pair = tc.pair;
   CUtensorMap ta, tb, tcm;
   if (make_tmap_im2col(&ta, X, Nb, H, W, C, R, S, pad_h, pad_w, stride, 128)) return 1;
-  if (make_tmap(&tb, Wk, K, O, K, 64, bn)) return 1;
+  if (make_tmap(&tb, Wk, K, O, K, 64, pair ? bn / 2 : bn)) return 1;
   if (y_layout != LYCO_NHWC && (P * Q) % 32)
     return fail("lyco_conv2d_fprop: NCHW output needs P*Q %% 32 == 0 (P*Q=%d)", P * Q);
   if (y_layout == LYCO_NCHW) {
@@ -485,17 +507,20 @@ int lyco_conv2d_fprop(const void* X, const void* Wk, void* Y, const void* bias, 
   lyco::ConvParams cp;
   cp.g.epi_pq = P * Q;
   cp.g.C = Y; cp.g.bias = bias; cp.g.ldc = O; cp.g.M = M; cp.g.N = O; cp.g.K = K;
-  cp.g.m_tiles = cdiv(M, 128); cp.g.n_tiles = cdiv(O, bn); cp.g.splits = 1; cp.g.k_blocks = R * S * (C / 64);
-  cp.g.block_n = bn; cp.g.stages = stages_for(false, bn);
+  cp.g.m_tiles = cdiv(M, pair ? 256 : 128); cp.g.n_tiles = cdiv(O, bn); cp.g.splits = 1;
+  cp.g.k_blocks = R * S * (C / 64);
+  cp.g.block_n = bn; cp.g.stages = stages_for(pair, bn);
   cp.g.fmt = (dtype == LYCO_BF16) ? 1 : 0; cp.g.bias_dtype = bias_dtype;
   cp.PQ = P * Q; cp.Q = Q; cp.C = C; cp.CB = C / 64; cp.S = S; cp.stride = stride;
   cp.low_w = -pad_w; cp.low_h = -pad_h; cp.tiles_per_tap = 1;
   const long total = static_cast<long>(cp.g.m_tiles) * cp.g.n_tiles;
-  const int grid = static_cast<int>(total < di.sms ? total : di.sms);
-  if (y_layout == LYCO_NCHW) return launch_conv<lyco::MODE_FPROP, lyco::EPI_STORE16_NCHW>(ta, tb, tcm, cp, grid, stream);
+  const long slots = pair ? di.sms / 2 : di.sms;
+  const int workers = static_cast<int>(total < slots ? total : slots);
+  if (y_layout == LYCO_NCHW)
+    return launch_conv<lyco::MODE_FPROP, lyco::EPI_STORE16_NCHW>(pair, ta, tb, tcm, cp, workers, stream);
   if (y_layout == LYCO_NCHW_F32)
-    return launch_conv<lyco::MODE_FPROP, lyco::EPI_STORE_F32_NCHW>(ta, tb, tcm, cp, grid, stream);
-  return launch_conv<lyco::MODE_FPROP, lyco::EPI_STORE16>(ta, tb, tcm, cp, grid, stream);
+    return launch_conv<lyco::MODE_FPROP, lyco::EPI_STORE_F32_NCHW>(pair, ta, tb, tcm, cp, workers, stream);
+  return launch_conv<lyco::MODE_FPROP, lyco::EPI_STORE16>(pair, ta, tb, tcm, cp, workers, stream);
 }
 
 int lyco_filter_relayout(const void* in, void* out, int O, int C, int taps, int mode, int dtype, void* stream_) {
@@ -573,19 +598,28 @@ int lyco_conv2d_wgrad(const void* X, const void* dY, float* dW, int Nb, int H, i
   const int64_t M64 = static_cast<int64_t>(Nb) * P * Q;
   if (M64 > (1ll << 30)) return fail("lyco_conv2d_wgrad: too many output pixels");
   const int Mpix = static_cast<int>(M64);
-  // N tile (64-column im2col atoms): least padding inside one filter tap per unit of tile cost
+  // Tile: N in 64-column im2col atoms inside one filter tap, M = 128 (one CTA) or 256 (CTA pair) output channels;
+  // least padding (channels past C in the last N tile of a tap, rows past O in the last M tile) per unit of tile cost.
   int bn = 64;
+  bool pair = false;
   double best = 1e30;
-  for (int c = 256; c >= 64; c -= 64) {
-    const double waste = static_cast<double>(cdiv(C, c) * c) / C;  // >= 1
-    const double cost = waste * tile_cost(false, c) / c;
-    if (cost < best * 0.995) { best = cost; bn = c; }
+  for (int pr = 1; pr >= 0; --pr) {
+    if (pr && (O <= 128 || !conv_pair_enabled())) continue;
+    for (int c = 256; c >= 64; c -= 64) {
+      if (!tile_valid(pr, c, true)) continue;
+      const int rows = pr ? 256 : 128;
+      const double waste = static_cast<double>(cdiv(C, c) * c) / C * (static_cast<double>(cdiv(O, rows) * rows) / O);
+      const double cost = waste * tile_cost(pr, c) / c;
+      if (cost < best * 0.995) { best = cost; bn = c; pair = pr != 0; }
+    }
   }
   const int tiles_per_tap = cdiv(C, bn);
   const int taps = R * S;
   const int k_blocks = cdiv(Mpix, 64);
-  const long tiles = static_cast<long>(cdiv(O, 128)) * taps * tiles_per_tap;
-  int splits = split_k > 0 ? split_k : pick_splits(tiles, k_blocks, di.sms);
+  const int m_tiles = cdiv(O, pair ? 256 : 128);
+  const long tiles = static_cast<long>(m_tiles) * taps * tiles_per_tap;
+  const long slots = pair ? di.sms / 2 : di.sms;
+  int splits = split_k > 0 ? split_k : pick_splits(tiles, k_blocks, static_cast<int>(slots));
   if (splits > k_blocks) splits = k_blocks;
   CUtensorMap ta, tb, tcm;
   memset(&tcm, 0, sizeof(tcm));
@@ -594,16 +628,16 @@ int lyco_conv2d_wgrad(const void* X, const void* dY, float* dW, int Nb, int H, i
   lyco::ConvParams cp;
   const int ldw = taps * C;
   cp.g.C = dW; cp.g.bias = nullptr; cp.g.ldc = ldw; cp.g.M = O; cp.g.N = ldw; cp.g.K = Mpix;
-  cp.g.m_tiles = cdiv(O, 128); cp.g.n_tiles = taps * tiles_per_tap; cp.g.splits = splits; cp.g.k_blocks = k_blocks;
-  cp.g.block_n = bn; cp.g.stages = stages_for(false, bn);
+  cp.g.m_tiles = m_tiles; cp.g.n_tiles = taps * tiles_per_tap; cp.g.splits = splits; cp.g.k_blocks = k_blocks;
+  cp.g.block_n = bn; cp.g.stages = stages_for(pair, bn);
   cp.g.fmt = (dtype == LYCO_BF16) ? 1 : 0; cp.g.bias_dtype = 0;
   cp.PQ = P * Q; cp.Q = Q; cp.C = C; cp.CB = C / 64; cp.S = S; cp.stride = stride;
   cp.low_w = -pad_w; cp.low_h = -pad_h; cp.tiles_per_tap = tiles_per_tap;
   if (splits > 1) LYCO_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * static_cast<size_t>(O) * ldw, stream));
   const long total = tiles * splits;
-  const int grid = static_cast<int>(total < di.sms ? total : di.sms);
-  if (splits > 1) return launch_conv<lyco::MODE_WGRAD, lyco::EPI_ATOMIC_F32>(ta, tb, tcm, cp, grid, stream);
-  return launch_conv<lyco::MODE_WGRAD, lyco::EPI_STORE_F32>(ta, tb, tcm, cp, grid, stream);
+  const int workers = static_cast<int>(total < slots ? total : slots);
+  if (splits > 1) return launch_conv<lyco::MODE_WGRAD, lyco::EPI_ATOMIC_F32>(pair, ta, tb, tcm, cp, workers, stream);
+  return launch_conv<lyco::MODE_WGRAD, lyco::EPI_STORE_F32>(pair, ta, tb, tcm, cp, workers, stream);
 }
 
 int lyco_merge_weight(const lyco_delta_desc_t* d, const void* W, void* W_out, void* stream_) {

@@ -213,3 +213,36 @@ def test_filter_relayouts_are_bit_exact(O, C, R, S):
     assert dw.shape == (O, C, R, S) and dw.is_contiguous()
     assert torch.equal(dw, dwk.view(O, R, S, C).permute(0, 3, 1, 2).contiguous())
     assert K._lib.launch_count() == before + 3  # all three ran on the engine
+
+
+@pytest.mark.parametrize("Nb,C,O,H,W,stride", [
+    (2, 128, 256, 16, 16, 1),    # CTA-pair tiles in fprop, dgrad and wgrad
+    (1, 320, 512, 12, 12, 1),    # N tile padding inside a tap (320 channels), two pair rows
+    (3, 640, 384, 8, 8, 1),      # O not a multiple of 256: ragged pair row
+    (2, 256, 1280, 8, 8, 2),     # stride 2 wgrad
+    (5, 64, 192, 10, 6, 1),      # pixels not a multiple of 128, ragged images
+])
+def test_conv_kernels_match_fp32_autograd(Nb, C, O, H, W, stride):
+    """fprop / dgrad-as-fprop / wgrad on shapes that select the CTA-pair kernels, against fp32 autograd of the
+    same bf16 operands (2^-7 relative at tensor scale: fp32 accumulation, one bf16 rounding)."""
+    import torch.nn.functional as F
+
+    from lycoris_b200.engine import kernels as K
+
+    torch.manual_seed(C + O)
+    x = torch.randn(Nb, C, H, W, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(O, C, 3, 3, device="cuda") * 0.05).to(torch.bfloat16)
+    xf, wf = x.float().requires_grad_(True), w.float().requires_grad_(True)
+    yf = F.conv2d(xf, wf, None, stride, 1)
+    dy = torch.randn_like(yf).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    yf.backward(dy.float())
+
+    y = K.conv2d_fprop(x, K.filter_relayout(w, K.FILTER_FPROP), None, 3, 3, (1, 1), stride)
+    yf = yf.detach()
+    assert float((y.float() - yf).abs().max()) <= 2 ** -7 * float(yf.abs().max())
+    dwk = K.conv2d_wgrad(x, dy, 3, 3, (1, 1), stride)
+    dw = K.filter_relayout((dwk, (O, C, 3, 3)), K.FILTER_WBACK)
+    assert float((dw - wf.grad).abs().max()) <= 1e-3 * float(wf.grad.abs().max())
+    if stride == 1:
+        dx = K.conv2d_fprop(dy, K.filter_relayout(w, K.FILTER_DGRAD), None, 3, 3, (1, 1), 1)
+        assert float((dx.float() - xf.grad).abs().max()) <= 2 ** -7 * float(xf.grad.abs().max())
