@@ -32,8 +32,8 @@ def main():
     x = torch.randn(Nb, C, H, H, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
     dy = torch.randn(Nb, O, H, H, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
     w = (torch.randn(O, C, 3, 3, device="cuda") * 0.01).to(torch.bfloat16)
-    wk = w.permute(0, 2, 3, 1).reshape(O, 9 * C)
-    wd = w.flip(2, 3).permute(1, 2, 3, 0).reshape(C, 9 * O)
+    wk = k.filter_relayout(w, k.FILTER_FPROP)
+    wd = k.filter_relayout(w, k.FILTER_DGRAD)
     for _ in range(reps):
         k.conv2d_fprop(x, wk, None, 3, 3, (1, 1), 1)
         k.conv2d_fprop(dy, wd, None, 3, 3, (1, 1), 1)
