@@ -1,0 +1,131 @@
+"""Generate tests/golden/network_side.pt from the REAL reference (build container only; needs
+/root/reference): network-level checkpoint round trip, merge and max-norm of SURVEY.md §8f rows 1-2 on the toy
+UNet, through `lycoris.kohya` exactly as kohya sd-scripts drives it:
+
+    create_network(...)                              -> state_dict() (the saved checkpoint)
+    create_network_from_weights(weights_sd=ckpt)     -> module list (names / classes / shapes) and its own state dict
+    network.merge_to(None, unet, ckpt, fp32, "cpu")  -> checksum of every base weight afterwards
+    network.apply_max_norm_regularization(v, "cpu")  -> (keys_scaled, mean_norm, max_norm) and the checkpoint afterwards
+
+The tests rebuild the same objects with lycoris_b200.kohya and compare.  Run: ``python oracle/gen_golden_network.py``.
+"""
+
+import logging
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(1, "/root/reference")
+
+import lycoris  # noqa: E402  (the reference)
+import lycoris.kohya  # noqa: E402
+
+from oracle.toy_models import ToyUNet  # noqa: E402
+
+logging.getLogger("LyCORIS").setLevel(logging.ERROR)
+OUT = os.path.join(ROOT, "tests", "golden", "network_side.pt")
+
+CASES = {
+    "lokr_full": dict(dim=100000, alpha=1, kw=dict(algo="lokr", factor=8, preset="full", conv_dim=100000, conv_alpha=1)),
+    "lokr_lowrank": dict(dim=2, alpha=1, kw=dict(algo="lokr", factor=4, preset="full", conv_dim=2, conv_alpha=1)),
+    "locon": dict(dim=8, alpha=4, kw=dict(algo="locon", preset="full", conv_dim=4, conv_alpha=1)),
+    "loha": dict(dim=8, alpha=4, kw=dict(algo="loha", preset="attn-mlp")),
+    "locon_dora": dict(dim=4, alpha=2, kw=dict(algo="locon", preset="attn-mlp", dora_wd=True)),
+}
+
+
+def make_network(kohya, case, seed=0):
+    torch.manual_seed(seed)
+    unet = ToyUNet()
+    torch.manual_seed(seed + 1)
+    net = kohya.create_network(1.0, case["dim"], case["alpha"], None, None, unet, **case["kw"])
+    net.apply_to(None, unet, False, True)  # registers the adapters on the network (kohya calls this next)
+    g = torch.Generator().manual_seed(seed + 2)
+    with torch.no_grad():
+        for p in net.parameters():
+            if float(p.abs().sum()) == 0.0:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.05)
+    return unet, net
+
+
+def base_checksums(unet):
+    return checksums(dict(unet.named_parameters()))
+
+
+def checksums(sd):
+    """(sum, sum of magnitudes) per tensor in float64 — enough to pin a derived state dict without storing it"""
+    return {k: [float(v.detach().double().sum()), float(v.detach().double().abs().sum())] for k, v in sd.items()}
+
+
+def sig(loras):
+    return [[l.lora_name, type(l).__name__, [[k, list(v.shape)] for k, v in l.state_dict().items()]] for l in loras]
+
+
+def snap(sd):
+    return {k: v.detach().clone() for k, v in sd.items()}
+
+
+def run(case):
+    out = {"case": case}
+    unet, net = make_network(lycoris.kohya, case)
+    assert len(list(net.parameters())) > 0
+    ckpt = snap(net.state_dict())
+    out["checkpoint"] = ckpt
+    out["modules"] = sig(net.loras)
+
+    # from-weights on a fresh copy of the base model
+    torch.manual_seed(0)
+    unet2 = ToyUNet()
+    net2, sd2 = lycoris.kohya.create_network_from_weights(1.0, None, None, None, unet2, weights_sd=snap(ckpt))
+    # NB `net2.loras` still holds what the constructor built under the class-level preset of the moment; the loaded
+    # adapters are `unet_loras` (they become `.loras` in apply_to)
+    out["rebuilt_modules"] = sig(net2.unet_loras)
+    # kohya's sequence: apply_to registers the rebuilt adapters, then load_state_dict(weights_sd) runs
+    net2.apply_to(None, unet2, False, True)
+    info = net2.load_state_dict(snap(ckpt), False)
+    out["rebuilt_missing"] = sorted(info.missing_keys)
+    out["rebuilt_unexpected"] = sorted(info.unexpected_keys)
+    out["rebuilt_checkpoint"] = checksums(net2.state_dict())
+
+    # merge into the base weights
+    torch.manual_seed(0)
+    unet3 = ToyUNet()
+    net3, _ = lycoris.kohya.create_network_from_weights(1.0, None, None, None, unet3, weights_sd=snap(ckpt),
+                                                         for_inference=True)
+    before = base_checksums(unet3)
+    net3.merge_to(None, unet3, snap(ckpt), torch.float32, "cpu")
+    after = base_checksums(unet3)
+    out["merge_changed"] = sorted(k for k in after if after[k] != before[k])
+    out["merge_checksums"] = {k: after[k] for k in out["merge_changed"]}
+
+    # max-norm regularisation on the trained network
+    unet4, net4 = make_network(lycoris.kohya, case)
+    norms = []
+    with torch.no_grad():
+        for l in net4.loras:
+            if hasattr(l, "get_diff_weight"):
+                try:
+                    norms.append(float(l.get_diff_weight(1.0)[0].norm()))
+                except Exception:  # noqa: BLE001
+                    pass
+    limit = sorted(norms)[len(norms) // 2]  # the median norm: about half of the modules get clamped
+    keys_scaled, mean_norm, max_norm = net4.apply_max_norm_regularization(limit, "cpu")
+    out["max_norm"] = {"limit": limit, "keys_scaled": int(keys_scaled), "mean_norm": float(mean_norm),
+                       "max_norm": float(max_norm), "checkpoint": checksums(net4.state_dict())}
+    return out
+
+
+def main():
+    cases = {name: run(c) for name, c in CASES.items()}
+    torch.save(cases, OUT)
+    print(f"{len(cases)} network cases -> {OUT} ({os.path.getsize(OUT) / 1024:.0f} KiB)")
+    for k, v in cases.items():
+        print("  ", k, len(v["modules"]), "modules; merged", len(v["merge_changed"]), "base tensors; max-norm scaled",
+              v["max_norm"]["keys_scaled"], "missing", len(v["rebuilt_missing"]), "unexpected", len(v["rebuilt_unexpected"]))
+
+
+if __name__ == "__main__":
+    main()

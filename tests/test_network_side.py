@@ -1,0 +1,117 @@
+"""Network-level checkpoint round trip, merge and max-norm through ``lycoris_b200.kohya`` against the REAL
+reference's outputs on the toy UNet (tests/golden/network_side.pt, written by oracle/gen_golden_network.py):
+SURVEY.md §8f rows 1-2 as kohya sd-scripts drives them.  Host-side logic, runs on the CPU."""
+import logging
+import os
+
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+CASES = torch.load(os.path.join(GOLDEN, "network_side.pt"), weights_only=False)
+IDS = sorted(CASES)
+logging.getLogger("LyCORIS").setLevel(logging.ERROR)
+
+
+def _toy(seed=0):
+    from oracle.toy_models import ToyUNet
+
+    torch.manual_seed(seed)
+    return ToyUNet()
+
+
+def _make_network(case, seed=0):
+    """Same construction sequence as oracle/gen_golden_network.py:make_network, with the product's kohya module."""
+    import lycoris_b200.kohya as kohya
+
+    unet = _toy(seed)
+    torch.manual_seed(seed + 1)
+    net = kohya.create_network(1.0, case["dim"], case["alpha"], None, None, unet, **case["kw"])
+    net.apply_to(None, unet, False, True)
+    g = torch.Generator().manual_seed(seed + 2)
+    with torch.no_grad():
+        for p in net.parameters():
+            if float(p.abs().sum()) == 0.0:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.05)
+    return unet, net
+
+
+def _sig(loras):
+    return [[l.lora_name, type(l).__name__, [[k, list(v.shape)] for k, v in l.state_dict().items()]] for l in loras]
+
+
+def _checksums(sd):
+    return {k: [float(v.detach().double().sum()), float(v.detach().double().abs().sum())] for k, v in sd.items()}
+
+
+def _close(a, b, what, rel=1e-5):
+    assert set(a) == set(b), (what, sorted(set(a) ^ set(b))[:6])
+    for k in b:
+        for x, y in zip(a[k], b[k]):
+            assert abs(x - y) <= rel * max(1.0, abs(y)), (what, k, x, y)
+
+
+def _snap(sd):
+    return {k: v.detach().clone() for k, v in sd.items()}
+
+
+@pytest.mark.parametrize("name", IDS)
+def test_trained_network_saves_the_reference_checkpoint(name):
+    """Same seeds, same construction: every key, shape and value of state_dict() equals the reference's."""
+    ref = CASES[name]
+    _, net = _make_network(ref["case"])
+    assert _sig(net.loras) == ref["modules"]
+    sd = net.state_dict()
+    assert list(sd.keys()) == list(ref["checkpoint"].keys())
+    for k, v in ref["checkpoint"].items():
+        assert sd[k].shape == v.shape and sd[k].dtype == v.dtype, k
+        assert torch.allclose(sd[k].detach(), v, rtol=1e-6, atol=1e-7), (k, float((sd[k].detach() - v).abs().max()))
+
+
+@pytest.mark.parametrize("name", IDS)
+def test_create_network_from_reference_checkpoint(name):
+    """create_network_from_weights on the reference's checkpoint: same module list as the reference's own loader,
+    nothing missing / unexpected on load, and the re-exported checkpoint matches."""
+    import lycoris_b200.kohya as kohya
+
+    ref = CASES[name]
+    unet = _toy()
+    net, sd = kohya.create_network_from_weights(1.0, None, None, None, unet, weights_sd=_snap(ref["checkpoint"]))
+    assert _sig(net.unet_loras) == ref["rebuilt_modules"]  # (.loras is only rebuilt from them in apply_to)
+    net.apply_to(None, unet, False, True)
+    assert _sig(net.loras) == ref["rebuilt_modules"]
+    info = net.load_state_dict(_snap(ref["checkpoint"]), False)
+    assert sorted(info.missing_keys) == ref["rebuilt_missing"]
+    assert sorted(info.unexpected_keys) == ref["rebuilt_unexpected"]
+    _close(_checksums(net.state_dict()), ref["rebuilt_checkpoint"], f"{name}: re-exported checkpoint")
+
+
+@pytest.mark.parametrize("name", IDS)
+def test_merge_to_base_model(name):
+    """for_inference load + merge_to: exactly the base tensors the reference touches end up with its values."""
+    import lycoris_b200.kohya as kohya
+
+    ref = CASES[name]
+    unet = _toy()
+    net, _ = kohya.create_network_from_weights(1.0, None, None, None, unet, weights_sd=_snap(ref["checkpoint"]),
+                                               for_inference=True)
+    before = _checksums(dict(unet.named_parameters()))
+    net.merge_to(None, unet, _snap(ref["checkpoint"]), torch.float32, "cpu")
+    after = _checksums(dict(unet.named_parameters()))
+    changed = sorted(k for k in after if after[k] != before[k])
+    assert changed == ref["merge_changed"]
+    _close({k: after[k] for k in changed}, ref["merge_checksums"], f"{name}: merged base weights")
+
+
+@pytest.mark.parametrize("name", IDS)
+def test_max_norm_regularisation(name):
+    """kohya's scale_weight_norms hook: same count of scaled modules, same mean / max norm, same parameters after."""
+    ref = CASES[name]
+    exp = ref["max_norm"]
+    _, net = _make_network(ref["case"])
+    keys_scaled, mean_norm, max_norm = net.apply_max_norm_regularization(exp["limit"], "cpu")
+    assert int(keys_scaled) == exp["keys_scaled"]
+    assert abs(float(mean_norm) - exp["mean_norm"]) <= 1e-5 * max(1.0, abs(exp["mean_norm"]))
+    assert abs(float(max_norm) - exp["max_norm"]) <= 1e-5 * max(1.0, abs(exp["max_norm"]))
+    _close(_checksums(net.state_dict()), exp["checkpoint"], f"{name}: checkpoint after max-norm")
