@@ -23,7 +23,7 @@ sys.path.insert(1, "/root/reference")
 import lycoris  # noqa: E402  (the reference)
 import lycoris.kohya  # noqa: E402
 
-from oracle.toy_models import ToyUNet  # noqa: E402
+from oracle.toy_models import ToyTextEncoder, ToyUNet  # noqa: E402
 
 logging.getLogger("LyCORIS").setLevel(logging.ERROR)
 OUT = os.path.join(ROOT, "tests", "golden", "network_side.pt")
@@ -118,11 +118,54 @@ def run(case):
     return out
 
 
+def run_text_encoders():
+    """Adapters on text encoders: one encoder -> `lora_te_*`, a list -> `lora_te1_*`,
+    `lora_te2_*`; trained checkpoint, from-weights rebuild, and the unet-only / te-only apply_to switches."""
+    out = {}
+    for tag, n_te in (("single", 1), ("pair", 2)):
+        torch.manual_seed(0)
+        unet = ToyUNet()
+        tes = [ToyTextEncoder(dim=32 + 16 * i) for i in range(n_te)]
+        te_arg = tes[0] if n_te == 1 else tes
+        torch.manual_seed(1)
+        net = lycoris.kohya.create_network(1.0, 4, 2, None, te_arg, unet, algo="lokr", factor=4, preset="attn-mlp")
+        rec = {"te_modules": sig(net.text_encoder_loras), "unet_modules": len(net.unet_loras)}
+        net.apply_to(te_arg, unet, True, True)
+        g = torch.Generator().manual_seed(2)
+        with torch.no_grad():
+            for p in net.parameters():
+                if float(p.abs().sum()) == 0.0:
+                    p.copy_(torch.randn(p.shape, generator=g) * 0.05)
+        ckpt = snap(net.state_dict())
+        rec["checkpoint"] = ckpt
+        # forward of the wrapped text encoder(s) with the trained adapters (fp32, CPU): parity target for the GPU tests
+        ids = torch.arange(12).view(2, 6) % 64
+        with torch.no_grad():
+            rec["ids"] = ids
+            rec["te_out"] = [te(ids).clone() for te in tes]
+        net.restore()
+        torch.manual_seed(0)
+        unet2 = ToyUNet()
+        tes2 = [ToyTextEncoder(dim=32 + 16 * i) for i in range(n_te)]
+        te2 = tes2[0] if n_te == 1 else tes2
+        net2, _ = lycoris.kohya.create_network_from_weights(1.0, None, None, te2, unet2, weights_sd=snap(ckpt))
+        rec["rebuilt_te_modules"] = sig(net2.text_encoder_loras)
+        rec["rebuilt_unet_modules"] = len(net2.unet_loras)
+        net2.apply_to(te2, unet2, True, False)  # text encoder only
+        rec["te_only_keys"] = list(net2.state_dict().keys())
+        out[tag] = rec
+    return out
+
+
 def main():
     cases = {name: run(c) for name, c in CASES.items()}
+    cases["text_encoders"] = run_text_encoders()
     torch.save(cases, OUT)
     print(f"{len(cases)} network cases -> {OUT} ({os.path.getsize(OUT) / 1024:.0f} KiB)")
     for k, v in cases.items():
+        if k == "text_encoders":
+            print("  ", k, {t: len(r["te_modules"]) for t, r in v.items()})
+            continue
         print("  ", k, len(v["modules"]), "modules; merged", len(v["merge_changed"]), "base tensors; max-norm scaled",
               v["max_norm"]["keys_scaled"], "missing", len(v["rebuilt_missing"]), "unexpected", len(v["rebuilt_unexpected"]))
 

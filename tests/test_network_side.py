@@ -10,7 +10,7 @@ import torch
 from conftest import GOLDEN
 
 CASES = torch.load(os.path.join(GOLDEN, "network_side.pt"), weights_only=False)
-IDS = sorted(CASES)
+IDS = sorted(k for k in CASES if k != "text_encoders")
 logging.getLogger("LyCORIS").setLevel(logging.ERROR)
 
 
@@ -115,3 +115,49 @@ def test_max_norm_regularisation(name):
     assert abs(float(mean_norm) - exp["mean_norm"]) <= 1e-5 * max(1.0, abs(exp["mean_norm"]))
     assert abs(float(max_norm) - exp["max_norm"]) <= 1e-5 * max(1.0, abs(exp["max_norm"]))
     _close(_checksums(net.state_dict()), exp["checkpoint"], f"{name}: checkpoint after max-norm")
+
+
+# ----------------------------------------------------------------------------- text encoders
+def _text_encoders(n):
+    from oracle.toy_models import ToyTextEncoder
+
+    tes = [ToyTextEncoder(dim=32 + 16 * i) for i in range(n)]
+    return tes, (tes[0] if n == 1 else tes)
+
+
+@pytest.mark.parametrize("tag,n_te", [("single", 1), ("pair", 2)])
+def test_text_encoder_adapters_match_reference(tag, n_te):
+    """One encoder -> `lora_te_*`, a list -> `lora_te1_*` / `lora_te2_*` (CLIPAttention / CLIPMLP discovery); the
+    trained checkpoint equals the reference's, the from-weights loader rebuilds the same modules, and
+    apply_to(text encoder only) registers only those."""
+    import lycoris_b200.kohya as kohya
+
+    ref = CASES["text_encoders"][tag]
+    unet = _toy()
+    tes, te_arg = _text_encoders(n_te)
+    torch.manual_seed(1)
+    net = kohya.create_network(1.0, 4, 2, None, te_arg, unet, algo="lokr", factor=4, preset="attn-mlp")
+    assert _sig(net.text_encoder_loras) == ref["te_modules"]
+    assert len(net.unet_loras) == ref["unet_modules"]
+    prefixes = {l.lora_name.split("_text_model")[0] for l in net.text_encoder_loras}
+    assert prefixes == ({"lora_te"} if n_te == 1 else {"lora_te1", "lora_te2"})
+    net.apply_to(te_arg, unet, True, True)
+    g = torch.Generator().manual_seed(2)
+    with torch.no_grad():
+        for p in net.parameters():
+            if float(p.abs().sum()) == 0.0:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.05)
+    sd = net.state_dict()
+    assert list(sd.keys()) == list(ref["checkpoint"].keys())
+    for k, v in ref["checkpoint"].items():
+        assert torch.allclose(sd[k].detach(), v, rtol=1e-6, atol=1e-7), k
+    net.restore()
+
+    unet2 = _toy()
+    _, te2 = _text_encoders(n_te)
+    net2, _ = kohya.create_network_from_weights(1.0, None, None, te2, unet2, weights_sd=_snap(ref["checkpoint"]))
+    assert _sig(net2.text_encoder_loras) == ref["rebuilt_te_modules"]
+    assert len(net2.unet_loras) == ref["rebuilt_unet_modules"]
+    net2.apply_to(te2, unet2, True, False)
+    assert list(net2.state_dict().keys()) == ref["te_only_keys"]
+    net2.restore()
