@@ -562,7 +562,7 @@ def run_reference_cpu(args):
     cfg = model_cfg(args.model)
     vals = []
     for _ in range(max(1, min(args.warmup, 1))):
-        cpu_reference(args, budget_s=5.0)
+        cpu_reference(args, budget_s=min(5.0, args.cpu_seconds))
     for _ in range(max(1, args.steps if args.steps < 3 else 3)):
         vals.append(cpu_reference(args, budget_s=args.cpu_seconds))
     best = max(vals, key=lambda r: r["value"])
@@ -571,8 +571,11 @@ def run_reference_cpu(args):
         "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000.0 * best["extrapolated_s_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-        "config": {"workload": f"{cfg.name}-unet-skeleton + lokr factor 8 full-dim, per-GPU batch {args.batch}, "
-                               "wrapped layers only, CPU, extrapolated from a bounded sample"},
+        # the engine arm's workload, timed on the host cores through the oracle port of the reference path
+        "config": {"workload": f"{cfg.name}-unet-skeleton + {args.algo} ({ALGO_NOTE[args.algo]}), preset full, "
+                               f"per-GPU batch {args.batch}, latents {args.sample_size or cfg.sample_size}^2, fwd+bwd, "
+                               "reference path (oracle port) on the host CPU, fp32",
+                   "global_batch": args.batch, "parallelism": "cpu", "sample": best["sample"]},
         "cpu_baseline": best,
         "e2e": {"value": best["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
