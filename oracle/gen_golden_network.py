@@ -161,6 +161,13 @@ def main():
     cases = {name: run(c) for name, c in CASES.items()}
     cases["text_encoders"] = run_text_encoders()
     torch.save(cases, OUT)
+    # the public preset tables (lycoris/config.py): data the drop-in has to reproduce key for key
+    import json
+
+    from lycoris.config import PRESET
+
+    with open(os.path.join(ROOT, "tests", "golden", "presets.json"), "w") as fh:
+        json.dump(PRESET, fh, indent=1, sort_keys=True)
     print(f"{len(cases)} network cases -> {OUT} ({os.path.getsize(OUT) / 1024:.0f} KiB)")
     for k, v in cases.items():
         if k == "text_encoders":

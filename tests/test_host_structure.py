@@ -187,3 +187,17 @@ def test_parametrize_api_registers():
     L.LoConModule.parametrize(lin, "weight", 1.0, 2, 1)
     assert torch.nn.utils.parametrize.is_parametrized(lin, "weight")
     assert lin.weight.shape == (8, 8)  # CPU get_merged_weight is plain PyTorch (cold path)
+
+
+def test_builtin_preset_tables_equal_the_reference():
+    """lycoris/config.py PRESET (names, keys, target class / module-name lists incl. the DiT, Flux, SD3, Wan, Qwen
+    and text-encoder class names) — the discovery lists that make other backbones work with no new math."""
+    import json
+    import os
+
+    from conftest import GOLDEN
+    from lycoris_b200.config import PRESET
+
+    with open(os.path.join(GOLDEN, "presets.json")) as fh:
+        ref = json.load(fh)
+    assert json.loads(json.dumps(PRESET, sort_keys=True)) == ref
