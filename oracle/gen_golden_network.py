@@ -157,9 +157,79 @@ def run_text_encoders():
     return out
 
 
+GENERIC_PRESET = {
+    "enable_conv": True, "target_module": ["Linear", "Conv2d"], "target_name": [], "module_algo_map": {},
+    "name_algo_map": {}, "exclude_name": [], "use_fnmatch": False, "lora_prefix": "lycoris",
+}
+
+
+def run_generic_wrapper():
+    """The model-agnostic API (`lycoris.wrapper`): create_lycoris -> checkpoint -> create_lycoris_from_weights,
+    on-the-fly merge / restore (inference-time merge without keeping the adapters attached), and the
+    torch parametrization entry point `Module.parametrize`."""
+    out = {}
+    for algo, kw in (("locon", dict(conv_dim=4, conv_alpha=1)), ("lokr", dict(factor=4))):
+        lycoris.wrapper.LycorisNetwork.apply_preset(dict(GENERIC_PRESET))
+        torch.manual_seed(0)
+        unet = ToyUNet()
+        torch.manual_seed(1)
+        net = lycoris.create_lycoris(unet, 1.0, linear_dim=4, linear_alpha=2, algo=algo, **kw)
+        net.apply_to()
+        g = torch.Generator().manual_seed(2)
+        with torch.no_grad():
+            for p in net.parameters():
+                if float(p.abs().sum()) == 0.0:
+                    p.copy_(torch.randn(p.shape, generator=g) * 0.05)
+        ckpt = snap(net.state_dict())
+        rec = {"kw": kw, "modules": sig(net.loras), "checkpoint": ckpt}
+        net.restore()
+        torch.manual_seed(0)
+        unet2 = ToyUNet()
+        net2, _ = lycoris.wrapper.create_lycoris_from_weights(0.8, None, unet2, weights_sd=snap(ckpt))
+        rec["rebuilt_modules"] = sig(net2.loras)
+        rec["rebuilt_algo_table"] = dict(net2.algo_table)
+        rec["rebuilt_multipliers"] = sorted({float(l.multiplier) for l in net2.loras})
+        before = base_checksums(unet2)
+        net2.onfly_merge(0.8)
+        merged = base_checksums(unet2)
+        rec["onfly_changed"] = sorted(k for k in merged if merged[k] != before[k])
+        rec["onfly_checksums"] = {k: merged[k] for k in rec["onfly_changed"]}
+        net2.onfly_restore()
+        restored = base_checksums(unet2)
+        # NB on the CPU `cached_org_weight = org_weight.data.cpu()` ALIASES the live weight (Tensor.cpu() is a no-op
+        # there), so the reference's onfly_restore gives back the merged values; on a GPU it restores.  Recorded as is.
+        rec["onfly_restored_exactly"] = restored == before
+        rec["onfly_after_restore"] = {k: restored[k] for k in rec["onfly_changed"]}
+        out[algo] = rec
+
+    # parametrization of a bare weight tensor (LycorisBaseModule.parametrize, base.py:199-247)
+    par = {}
+    for name, cls, args, kw in (
+        ("locon", lycoris.modules.LoConModule, (1.0, 4, 2.0), {}),
+        ("lokr", lycoris.modules.LokrModule, (1.0, 2, 1.0), {"factor": 4}),
+        ("loha_conv", lycoris.modules.LohaModule, (1.0, 4, 2.0), {}),
+    ):
+        torch.manual_seed(3)
+        host = torch.nn.Conv2d(8, 16, 3) if name.endswith("conv") else torch.nn.Linear(24, 40)
+        w0 = host.weight.detach().clone()
+        torch.manual_seed(4)
+        mod = cls.parametrize(host, "weight", *args, **kw)
+        g = torch.Generator().manual_seed(5)
+        with torch.no_grad():
+            for p in mod.parameters():
+                if float(p.abs().sum()) == 0.0:
+                    p.copy_(torch.randn(p.shape, generator=g) * 0.05)
+        par[name] = {"w0": w0, "params": snap(dict(mod.named_parameters())),
+                     "weight": host.weight.detach().clone(),
+                     "param_names": sorted(n for n, _ in host.named_parameters())}
+    out["parametrize"] = par
+    return out
+
+
 def main():
     cases = {name: run(c) for name, c in CASES.items()}
     cases["text_encoders"] = run_text_encoders()
+    cases["generic_wrapper"] = run_generic_wrapper()
     torch.save(cases, OUT)
     # the public preset tables (lycoris/config.py): data the drop-in has to reproduce key for key
     import json
@@ -172,6 +242,10 @@ def main():
     for k, v in cases.items():
         if k == "text_encoders":
             print("  ", k, {t: len(r["te_modules"]) for t, r in v.items()})
+            continue
+        if k == "generic_wrapper":
+            print("  ", k, {t: (len(r["modules"]), len(r["onfly_changed"]), r["onfly_restored_exactly"])
+                            for t, r in v.items() if t != "parametrize"}, sorted(v["parametrize"]))
             continue
         print("  ", k, len(v["modules"]), "modules; merged", len(v["merge_changed"]), "base tensors; max-norm scaled",
               v["max_norm"]["keys_scaled"], "missing", len(v["rebuilt_missing"]), "unexpected", len(v["rebuilt_unexpected"]))

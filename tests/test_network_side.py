@@ -10,7 +10,7 @@ import torch
 from conftest import GOLDEN
 
 CASES = torch.load(os.path.join(GOLDEN, "network_side.pt"), weights_only=False)
-IDS = sorted(k for k in CASES if k != "text_encoders")
+IDS = sorted(k for k in CASES if k not in ("text_encoders", "generic_wrapper"))
 logging.getLogger("LyCORIS").setLevel(logging.ERROR)
 
 
@@ -161,3 +161,74 @@ def test_text_encoder_adapters_match_reference(tag, n_te):
     net2.apply_to(te2, unet2, True, False)
     assert list(net2.state_dict().keys()) == ref["te_only_keys"]
     net2.restore()
+
+
+# ------------------------------------------------------------------- model-agnostic wrapper (lycoris.wrapper)
+GENERIC_PRESET = {
+    "enable_conv": True, "target_module": ["Linear", "Conv2d"], "target_name": [], "module_algo_map": {},
+    "name_algo_map": {}, "exclude_name": [], "use_fnmatch": False, "lora_prefix": "lycoris",
+}
+
+
+@pytest.mark.parametrize("algo", ["locon", "lokr"])
+def test_generic_wrapper_checkpoint_from_weights_and_onfly_merge(algo):
+    import lycoris_b200 as L
+    from lycoris_b200.wrapper import LycorisNetwork, create_lycoris_from_weights
+
+    ref = CASES["generic_wrapper"][algo]
+    LycorisNetwork.apply_preset(dict(GENERIC_PRESET))
+    unet = _toy()
+    torch.manual_seed(1)
+    net = L.create_lycoris(unet, 1.0, linear_dim=4, linear_alpha=2, algo=algo, **ref["kw"])
+    net.apply_to()
+    g = torch.Generator().manual_seed(2)
+    with torch.no_grad():
+        for p in net.parameters():
+            if float(p.abs().sum()) == 0.0:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.05)
+    assert _sig(net.loras) == ref["modules"]
+    sd = net.state_dict()
+    assert list(sd.keys()) == list(ref["checkpoint"].keys())
+    for k, v in ref["checkpoint"].items():
+        assert torch.allclose(sd[k].detach(), v, rtol=1e-6, atol=1e-7), k
+    net.restore()
+
+    unet2 = _toy()
+    net2, _ = create_lycoris_from_weights(0.8, None, unet2, weights_sd=_snap(ref["checkpoint"]))
+    assert _sig(net2.loras) == ref["rebuilt_modules"]
+    assert dict(net2.algo_table) == ref["rebuilt_algo_table"]
+    assert sorted({float(l.multiplier) for l in net2.loras}) == ref["rebuilt_multipliers"]
+    before = _checksums(dict(unet2.named_parameters()))
+    net2.onfly_merge(0.8)
+    merged = _checksums(dict(unet2.named_parameters()))
+    changed = sorted(k for k in merged if merged[k] != before[k])
+    assert changed == ref["onfly_changed"]
+    _close({k: merged[k] for k in changed}, ref["onfly_checksums"], f"{algo}: on-the-fly merged weights")
+    net2.onfly_restore()
+    restored = _checksums(dict(unet2.named_parameters()))
+    # same behaviour as the reference on this device, including its CPU aliasing quirk (see the generator)
+    _close({k: restored[k] for k in changed}, ref["onfly_after_restore"], f"{algo}: after onfly_restore")
+
+
+@pytest.mark.parametrize("name", ["locon", "lokr", "loha_conv"])
+def test_parametrize_entry_point(name):
+    """`Module.parametrize(host, "weight", ...)`: the host's weight becomes W + dW through torch's parametrization
+    machinery; same parameter names and the same parametrized weight as the reference."""
+    import lycoris_b200.modules as M
+
+    ref = CASES["generic_wrapper"]["parametrize"][name]
+    cls, args, kw = {"locon": (M.LoConModule, (1.0, 4, 2.0), {}), "lokr": (M.LokrModule, (1.0, 2, 1.0), {"factor": 4}),
+                     "loha_conv": (M.LohaModule, (1.0, 4, 2.0), {})}[name]
+    torch.manual_seed(3)
+    host = torch.nn.Conv2d(8, 16, 3) if name.endswith("conv") else torch.nn.Linear(24, 40)
+    assert torch.equal(host.weight.detach(), ref["w0"])
+    torch.manual_seed(4)
+    mod = cls.parametrize(host, "weight", *args, **kw)
+    own = dict(mod.named_parameters())
+    assert set(own) == set(ref["params"])
+    with torch.no_grad():
+        for k, v in ref["params"].items():
+            own[k].copy_(v)
+    assert sorted(n for n, _ in host.named_parameters()) == ref["param_names"]
+    assert torch.allclose(host.weight.detach(), ref["weight"], rtol=1e-5, atol=1e-6)
+    assert not torch.equal(host.weight.detach(), ref["w0"])
