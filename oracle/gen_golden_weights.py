@@ -53,6 +53,11 @@ CASES = {
     "ia3_out": dict(cls="IA3Module", dim=4, alpha=1.0, kw={"train_on_input": False}),
     "ia3_in": dict(cls="IA3Module", dim=4, alpha=1.0, kw={"train_on_input": True}),
     "dylora": dict(cls="DyLoraModule", dim=8, alpha=4.0, kw={"block_size": 2}),
+    # rank dropout: Bernoulli mask over dW rows, drawn from torch's global RNG in training mode
+    "locon_rankdrop": dict(cls="LoConModule", dim=4, alpha=2.0, kw={}, rank_dropout=0.5),
+    "locon_rankdrop_scaled": dict(cls="LoConModule", dim=4, alpha=2.0, kw={"rank_dropout_scale": True}, rank_dropout=0.5),
+    "loha_rankdrop": dict(cls="LohaModule", dim=4, alpha=2.0, kw={}, rank_dropout=0.5),
+    "lokr_rankdrop": dict(cls="LokrModule", dim=100000, alpha=1.0, kw={"factor": 4}, rank_dropout=0.5),
 }
 
 
@@ -62,7 +67,8 @@ def build(c, layer_key, seed, bypass=None):
     kw = dict(c["kw"])
     if bypass is not None:
         kw["bypass_mode"] = bypass
-    mod = CLS[c["cls"]]("case", base, 1.0, c["dim"], c["alpha"], 0.0, 0.0, 0.0, c.get("use_tucker", False), **kw)
+    mod = CLS[c["cls"]]("case", base, 1.0, c["dim"], c["alpha"], 0.0, c.get("rank_dropout", 0.0), 0.0,
+                        c.get("use_tucker", False), **kw)
     perturb(mod, seed + 2)
     if isinstance(getattr(mod, "scalar", None), nn.Parameter):
         with torch.no_grad():
@@ -74,6 +80,11 @@ def snap(sd):
     return {k: v.detach().clone() for k, v in sd.items()}
 
 
+def checksums(sd):
+    """(sum, sum of magnitudes) per tensor in float64: pins a derived state dict without storing it again"""
+    return {k: [float(v.detach().double().sum()), float(v.detach().double().abs().sum())] for k, v in sd.items()}
+
+
 def try_call(fn, *a, **k):
     try:
         return fn(*a, **k)
@@ -83,7 +94,7 @@ def try_call(fn, *a, **k):
 
 def run(name, c, layer_key, seed):
     out = {"meta": dict(cls=c["cls"], dim=c["dim"], alpha=c["alpha"], kw=c["kw"], use_tucker=c.get("use_tucker", False),
-                        layer=layer_key, layer_spec=LAYERS[layer_key], seed=seed)}
+                        layer=layer_key, layer_spec=LAYERS[layer_key], seed=seed, rank_dropout=c.get("rank_dropout", 0.0))}
     base, mod = build(c, layer_key, seed)
     out["weight"] = base.weight.detach().clone()
     out["bias"] = base.bias.detach().clone()
@@ -101,6 +112,13 @@ def run(name, c, layer_key, seed):
         r = try_call(mod.merge_to, 0.5)
         out["merge_to_0p5"] = r if isinstance(r, dict) else {"weight": base.weight.detach().clone(),
                                                                "bias": base.bias.detach().clone()}
+    if c.get("rank_dropout", 0.0):
+        # training mode: the mask comes from torch's RNG — same seed, same rows dropped
+        mod.train()
+        torch.manual_seed(seed + 9)
+        with torch.no_grad():
+            out["train_diff"] = mod.get_diff_weight(1.0)[0].clone()
+        mod.eval()
     # the module rebuilt from its own checkpoint (create_network_from_weights' per-layer step)
     if c["cls"] not in ("IA3Module",):  # quirk 1: IA3's loader has an arity bug in the reference
         from lycoris.modules import get_module, make_module
@@ -115,22 +133,25 @@ def run(name, c, layer_key, seed):
             random.seed(seed + 5)
             with torch.no_grad():
                 return {"cls": type(m2).__name__, "diff_0p7": m2.get_diff_weight(0.7)[0].clone(),
-                        "state_dict": snap(m2.state_dict())}
+                        "state_dict": checksums(m2.state_dict())}
 
         out["rebuilt"] = try_call(rebuild)
     # max-norm on a fresh copy; the limit is chosen below the current norm so the clamp engages
     if hasattr(mod, "apply_max_norm"):
         base, mod = build(c, layer_key, seed)
+        mod.eval()
         with torch.no_grad():
             cur = float(mod.get_diff_weight(1.0)[0].norm())
+        mod.train()  # kohya calls it on the training network: rank dropout (if any) draws from torch's RNG
         limit = max(cur * 0.5, 1e-4)
+        torch.manual_seed(seed + 8)
         res = try_call(mod.apply_max_norm, limit, None)
         if isinstance(res, dict):
             out["max_norm"] = res
         else:
             scaled, norm = res
             out["max_norm"] = {"limit": limit, "scaled": bool(scaled), "norm": None if norm is None else torch.as_tensor(norm).detach().clone(),
-                               "state_dict": snap(mod.state_dict()), "params": snap(dict(mod.named_parameters()))}
+                               "state_dict": checksums(mod.state_dict()), "params": snap(dict(mod.named_parameters()))}
     # bypass mode, fp32, training
     base, mod = build(c, layer_key, seed, bypass=True)
     mod.apply_to()
@@ -141,6 +162,7 @@ def run(name, c, layer_key, seed):
     x = torch.randn(LAYERS[layer_key]["x"], generator=g)
     xr = x.clone().requires_grad_(True)
     random.seed(seed + 4)
+    torch.manual_seed(seed + 10)  # rank dropout in bypass mode masks the rank dimension from torch's RNG
     y = try_call(base, xr)
     if isinstance(y, dict):
         out["bypass"] = y

@@ -42,8 +42,8 @@ def build_product_module(case, base):
     meta = case["meta"]
     cls = {"LoConModule": M.LoConModule, "LohaModule": M.LohaModule, "LokrModule": M.LokrModule,
            "IA3Module": M.IA3Module, "DyLoraModule": M.DyLoraModule}[meta["cls"]]
-    mod = cls("case", base, meta.get("multiplier", 1.0), meta["dim"], meta["alpha"], 0.0, 0.0, 0.0,
-              meta.get("use_tucker", False), **meta["kw"])
+    mod = cls("case", base, meta.get("multiplier", 1.0), meta["dim"], meta["alpha"], 0.0, meta.get("rank_dropout", 0.0),
+              0.0, meta.get("use_tucker", False), **meta["kw"])
     own = dict(mod.named_parameters())
     assert set(own) == set(case["params"]), (sorted(own), sorted(case["params"]))
     with torch.no_grad():

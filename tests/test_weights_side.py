@@ -37,6 +37,15 @@ def _same(a, b, what):
     assert torch.allclose(a, b, **TOL), (what, float((a - b).abs().max()))
 
 
+def _same_sums(sd, sums, what, rel=1e-5):
+    """state dict against the (sum, sum of magnitudes) pairs the generator stored for it"""
+    assert set(sd) == set(sums), (what, sorted(set(sd) ^ set(sums)))
+    for k, (s0, s1) in sums.items():
+        v = sd[k].detach().double()
+        assert abs(float(v.sum()) - s0) <= rel * max(1.0, abs(s0)), (what, k)
+        assert abs(float(v.abs().sum()) - s1) <= rel * max(1.0, abs(s1)), (what, k)
+
+
 def _call_or_raises(expected, fn, *args):
     """Run ``fn``; when the reference raised, the product has to raise the same exception type."""
     if isinstance(expected, dict) and "raises" in expected:
@@ -98,6 +107,8 @@ def test_apply_max_norm(name):
     if "raises" in exp:
         _call_or_raises(exp, mod.apply_max_norm, 1e-3, None)
         return
+    mod.train()
+    torch.manual_seed(case["meta"]["seed"] + 8)
     scaled, norm = mod.apply_max_norm(exp["limit"], None)
     if exp["norm"] is None:  # adapters without a norm clamp (IA3, DyLoRA) answer (None, None)
         assert scaled is None and norm is None
@@ -106,9 +117,7 @@ def test_apply_max_norm(name):
     _same(torch.as_tensor(norm).detach(), exp["norm"], f"{name}: norm")
     for k, v in exp["params"].items():
         _same(dict(mod.named_parameters())[k].detach(), v, f"{name}: {k} after max-norm")
-    sd = mod.state_dict()
-    for k, v in exp["state_dict"].items():
-        _same(sd[k].detach(), v, f"{name}: state_dict[{k}] after max-norm")
+    _same_sums(mod.state_dict(), exp["state_dict"], f"{name}: state_dict after max-norm")
 
 
 @pytest.mark.parametrize("name", IDS)
@@ -138,6 +147,7 @@ def test_bypass_mode_forward_backward(name):
             return
         x = exp["x"].clone().requires_grad_(True)
         random.seed(exp["rand_seed"])
+        torch.manual_seed(case["meta"]["seed"] + 10)
         y = base(x)
         y.backward(exp["dy"])
         _same(y.detach(), exp["y"], f"{name}: y")
@@ -178,5 +188,29 @@ def test_module_rebuilt_from_reference_checkpoint(name):
     _same(diff, exp["diff_0p7"], f"{name}: dW of the rebuilt module")
     sd2 = mod.state_dict()
     assert list(sd2.keys()) == list(exp["state_dict"].keys())
-    for k, v in exp["state_dict"].items():
-        _same(sd2[k].detach(), v, f"{name}: re-exported {k}")
+    _same_sums(sd2, exp["state_dict"], f"{name}: re-exported checkpoint")
+
+
+@pytest.mark.parametrize("name", [n for n in IDS if "train_diff" in CASES[n]])
+def test_rank_dropout_mask_in_training_mode(name):
+    """Rebuild-mode rank dropout: the Bernoulli row mask is drawn from torch's global RNG exactly like the
+    reference does (same call, same shape), so with the same seed the same rows of dW are dropped."""
+    case = CASES[name]
+    base = build_base(case)
+    import lycoris_b200.modules as M
+
+    meta = case["meta"]
+    cls = {"LoConModule": M.LoConModule, "LohaModule": M.LohaModule, "LokrModule": M.LokrModule}[meta["cls"]]
+    mod = cls("case", base, 1.0, meta["dim"], meta["alpha"], 0.0, meta["rank_dropout"], 0.0, meta["use_tucker"],
+              **meta["kw"])
+    own = dict(mod.named_parameters())
+    with torch.no_grad():
+        for k, v in case["params"].items():
+            own[k].copy_(v)
+    mod.train()
+    torch.manual_seed(meta["seed"] + 9)
+    with torch.no_grad():
+        diff = mod.get_diff_weight(1.0)[0]
+    _same(diff, case["train_diff"], f"{name}: dW with rank dropout")
+    zero_rows = (case["train_diff"].flatten(1).abs().sum(1) == 0)
+    assert 0 < int(zero_rows.sum()) < zero_rows.numel(), "the fixture mask should drop some rows, not all"
