@@ -157,6 +157,47 @@ def run_text_encoders():
     return out
 
 
+def run_optimizer_groups():
+    """prepare_optimizer_params as kohya calls it: group count, lr, parameter count and numel per group, and the
+    lr descriptions, for plain / LoRA+ / text-encoder-specific learning rates."""
+    out = {}
+    torch.manual_seed(0)
+    unet = ToyUNet()
+    te = ToyTextEncoder()
+    torch.manual_seed(1)
+    net = lycoris.kohya.create_network(1.0, 4, 2, None, te, unet, algo="locon", preset="attn-mlp")
+    net.apply_to(te, unet, True, True)
+
+    def groups(res):
+        params, descriptions = res if isinstance(res, tuple) else (res, None)
+        return {"groups": [[float(g["lr"]), len(list(g["params"])), int(sum(p.numel() for p in g["params"]))]
+                           for g in params], "descriptions": descriptions}
+
+    out["plain"] = groups(net.prepare_optimizer_params(5e-5, 1e-4, 2e-4))
+    out["unet_only_lr"] = groups(net.prepare_optimizer_params(None, 1e-4, None))
+    net.set_loraplus_lr_ratio(4.0, None, None)
+    out["loraplus"] = groups(net.prepare_optimizer_params(5e-5, 1e-4, 2e-4))
+    net.set_loraplus_lr_ratio(None, 8.0, 2.0)
+    out["loraplus_split"] = groups(net.prepare_optimizer_params(5e-5, 1e-4, 2e-4))
+    net.restore()
+    return out
+
+
+def run_fnmatch_preset():
+    """name / module maps with shell-style patterns (use_fnmatch) through the generic wrapper"""
+    preset = {
+        "enable_conv": True, "target_module": ["Transformer2DModel"], "target_name": ["conv_*", "*time_emb_proj"],
+        "module_algo_map": {"FeedForward": {"algo": "lokr", "factor": 4, "dim": 100000}},
+        "name_algo_map": {"*attn2.to_?": {"algo": "loha", "dim": 2}, "conv_in": {"algo": "locon", "dim": 2}},
+        "exclude_name": ["*to_out*"], "use_fnmatch": True, "lora_prefix": "lycoris",
+    }
+    lycoris.wrapper.LycorisNetwork.apply_preset(dict(preset))
+    torch.manual_seed(0)
+    net = lycoris.wrapper.LycorisNetwork(ToyUNet(), 1.0, 8, 4, 1, 1, network_module="locon")
+    lycoris.wrapper.LycorisNetwork.apply_preset(dict(GENERIC_PRESET))
+    return {"preset": preset, "sig": sig(net.loras)}
+
+
 GENERIC_PRESET = {
     "enable_conv": True, "target_module": ["Linear", "Conv2d"], "target_name": [], "module_algo_map": {},
     "name_algo_map": {}, "exclude_name": [], "use_fnmatch": False, "lora_prefix": "lycoris",
@@ -230,6 +271,8 @@ def main():
     cases = {name: run(c) for name, c in CASES.items()}
     cases["text_encoders"] = run_text_encoders()
     cases["generic_wrapper"] = run_generic_wrapper()
+    cases["optimizer_groups"] = run_optimizer_groups()
+    cases["fnmatch_preset"] = run_fnmatch_preset()
     torch.save(cases, OUT)
     # the public preset tables (lycoris/config.py): data the drop-in has to reproduce key for key
     import json
@@ -242,6 +285,9 @@ def main():
     for k, v in cases.items():
         if k == "text_encoders":
             print("  ", k, {t: len(r["te_modules"]) for t, r in v.items()})
+            continue
+        if k in ("optimizer_groups", "fnmatch_preset"):
+            print("  ", k, {t: r for t, r in v.items() if t != "sig"} if k == "optimizer_groups" else len(v["sig"]))
             continue
         if k == "generic_wrapper":
             print("  ", k, {t: (len(r["modules"]), len(r["onfly_changed"]), r["onfly_restored_exactly"])

@@ -10,7 +10,7 @@ import torch
 from conftest import GOLDEN
 
 CASES = torch.load(os.path.join(GOLDEN, "network_side.pt"), weights_only=False)
-IDS = sorted(k for k in CASES if k not in ("text_encoders", "generic_wrapper"))
+IDS = sorted(k for k in CASES if "checkpoint" in CASES[k] and "max_norm" in CASES[k])
 logging.getLogger("LyCORIS").setLevel(logging.ERROR)
 
 
@@ -232,3 +232,45 @@ def test_parametrize_entry_point(name):
     assert sorted(n for n, _ in host.named_parameters()) == ref["param_names"]
     assert torch.allclose(host.weight.detach(), ref["weight"], rtol=1e-5, atol=1e-6)
     assert not torch.equal(host.weight.detach(), ref["w0"])
+
+
+def test_optimizer_param_groups_match_reference():
+    """prepare_optimizer_params (plain, unet-only, LoRA+ with one ratio, LoRA+ with separate unet / text-encoder
+    ratios): same groups, learning rates, parameter counts and descriptions as the reference."""
+    import lycoris_b200.kohya as kohya
+    from oracle.toy_models import ToyTextEncoder
+
+    ref = CASES["optimizer_groups"]
+    unet = _toy()
+    te = ToyTextEncoder()
+    torch.manual_seed(1)
+    net = kohya.create_network(1.0, 4, 2, None, te, unet, algo="locon", preset="attn-mlp")
+    net.apply_to(te, unet, True, True)
+
+    def groups(res):
+        params, descriptions = res if isinstance(res, tuple) else (res, None)
+        return {"groups": [[float(g["lr"]), len(list(g["params"])), int(sum(p.numel() for p in g["params"]))]
+                           for g in params], "descriptions": descriptions}
+
+    assert groups(net.prepare_optimizer_params(5e-5, 1e-4, 2e-4)) == ref["plain"]
+    assert groups(net.prepare_optimizer_params(None, 1e-4, None)) == ref["unet_only_lr"]
+    net.set_loraplus_lr_ratio(4.0, None, None)
+    assert groups(net.prepare_optimizer_params(5e-5, 1e-4, 2e-4)) == ref["loraplus"]
+    net.set_loraplus_lr_ratio(None, 8.0, 2.0)
+    assert groups(net.prepare_optimizer_params(5e-5, 1e-4, 2e-4)) == ref["loraplus_split"]
+    net.restore()
+
+
+def test_fnmatch_preset_selects_the_reference_modules():
+    """use_fnmatch: shell-style patterns in target_name / name_algo_map / exclude_name (docs/Preset.md)."""
+    from lycoris_b200.wrapper import LycorisNetwork
+
+    ref = CASES["fnmatch_preset"]
+    LycorisNetwork.apply_preset(dict(ref["preset"]))
+    try:
+        torch.manual_seed(0)
+        net = LycorisNetwork(_toy(), 1.0, 8, 4, 1, 1, network_module="locon")
+    finally:
+        LycorisNetwork.apply_preset(dict(GENERIC_PRESET))
+    assert _sig(net.loras) == ref["sig"]
+    assert {"LoConModule", "LokrModule"} <= {s[1] for s in ref["sig"]}  # the module_algo_map override took effect
