@@ -428,30 +428,38 @@ __global__ void __launch_bounds__(256) grad_lokr_kernel(lyco_delta_desc_t d, con
   }
   const int lane = threadIdx.x & 31;
   const float* row = dW + static_cast<int64_t>(pu * d.vp + pv) * K + v;
-  for (int u = 0; u < d.uq; ++u) {
-    float g[VEC];
-    if (live) {
+  // Groups of four w1 columns: the four (read-only) row loads of a group are issued before the first shuffle tree, so
+  // a thread keeps 64 bytes in flight instead of 16.  Per-u arithmetic and its order are unchanged.
+  constexpr int UG = 4;
+  for (int u0 = 0; u0 < d.uq; u0 += UG) {
+    float g[UG][VEC];
+#pragma unroll
+    for (int j = 0; j < UG; ++j) {
+      const bool on = live && (u0 + j < d.uq);
       if (VEC == 4) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(row + static_cast<int64_t>(u) * d.vq));
-        g[0] = t.x; g[1 % VEC] = t.y; g[2 % VEC] = t.z; g[3 % VEC] = t.w;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (on) t = __ldg(reinterpret_cast<const float4*>(row + static_cast<int64_t>(u0 + j) * d.vq));
+        g[j][0] = t.x; g[j][1 % VEC] = t.y; g[j][2 % VEC] = t.z; g[j][3 % VEC] = t.w;
       } else {
-        g[0] = __ldg(row + static_cast<int64_t>(u) * d.vq);
+        g[j][0] = on ? __ldg(row + static_cast<int64_t>(u0 + j) * d.vq) : 0.f;
       }
-    } else {
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) g[i] = 0.f;
-    }
-    const float a = rnd(ld_f(d.f0, d.f_dtype, pu * d.uq + u), fround);
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      g[i] *= gscale;
-      acc[i] = fmaf(a, g[i], acc[i]);
-      s = fmaf(g[i], b[i], s);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) atomicAdd(&s_w1[u], s);
+    for (int j = 0; j < UG; ++j) {
+      const int u = u0 + j;
+      if (u >= d.uq) break;  // warp-uniform
+      const float a = rnd(ld_f(d.f0, d.f_dtype, pu * d.uq + u), fround);
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const float gi = g[j][i] * gscale;
+        acc[i] = fmaf(a, gi, acc[i]);
+        s = fmaf(gi, b[i], s);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) atomicAdd(&s_w1[u], s);
+    }
   }
   if (live) {
 #pragma unroll
