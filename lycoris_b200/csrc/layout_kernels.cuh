@@ -36,6 +36,43 @@ transpose_cast_kernel(const SRC* __restrict__ src, uint16_t* __restrict__ dst, i
   uint16_t* d = dst + blockIdx.z * plane;
   const bool vec_in = (cols % 2 == 0), vec_out = (rows % 2 == 0);
 
+  // Interior tiles (the whole 64x64 tile inside the matrix, 16-byte alignable pitches): 16-byte global accesses on
+  // both sides.  Thread t loads 8 consecutive columns of row t/8 (+32), scatters them into the TRANSPOSED tile
+  // (tile_t[c][r], pitch 66 halfwords), then reads 8 consecutive rows of one column as four 32-bit words
+  // (bank = (c + 4*rg + q) mod 32: conflict-free) and writes them with one 16-byte store.
+  if (r0 + TR_TILE <= rows && c0 + TR_TILE <= cols && cols % 8 == 0 && rows % 8 == 0) {
+    uint16_t (*tile_t)[TR_TILE + 2] = tile;  // same storage, indexed [c][r]
+    const int t = ty * 32 + tx;
+    const int cg = t & 7, rr = t >> 3;  // 8 column groups x 32 rows per pass
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      const int r = rr + 32 * pass;
+      const SRC* q = s + static_cast<size_t>(r0 + r) * cols + c0 + 8 * cg;
+      uint16_t h[8];
+      if (sizeof(SRC) == 4) {
+        const float4 a = *reinterpret_cast<const float4*>(q);
+        const float4 b = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(q) + 4);
+        h[0] = to16<float>(a.x, fmt); h[1] = to16<float>(a.y, fmt); h[2] = to16<float>(a.z, fmt);
+        h[3] = to16<float>(a.w, fmt); h[4] = to16<float>(b.x, fmt); h[5] = to16<float>(b.y, fmt);
+        h[6] = to16<float>(b.z, fmt); h[7] = to16<float>(b.w, fmt);
+      } else {
+        *reinterpret_cast<uint4*>(h) = *reinterpret_cast<const uint4*>(q);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) tile_t[8 * cg + j][r] = h[j];
+    }
+    __syncthreads();
+    const int rg = t & 7, cc = t >> 3;  // 8 row groups x 32 columns per pass
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      const int c = cc + 32 * pass;
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(&tile_t[c][8 * rg]);
+      const uint4 v = make_uint4(w[0], w[1], w[2], w[3]);
+      *reinterpret_cast<uint4*>(d + static_cast<size_t>(c0 + c) * rows + r0 + 8 * rg) = v;
+    }
+    return;
+  }
+
 #pragma unroll
   for (int i = ty; i < TR_TILE; i += 8) {
     const int r = r0 + i, c = c0 + 2 * tx;

@@ -666,7 +666,17 @@ int lyco_merge_weight(const lyco_delta_desc_t* d, const void* W, void* W_out, vo
       int grid = static_cast<int>((work + 255) / 256);
       const int cap = di.sms * 16;
       if (grid > cap) grid = cap;
-      if (vec) lyco::merge_lokr_kernel<8><<<grid, 256, 0, stream>>>(*d, w, wo);
+      // the two regimes of kohya training get dtype-specialised instantiations (same source, constants folded);
+      // LYCO_MERGE_GENERIC=1 keeps everything on the run-time-dtype kernel for A/B and bit-exactness checks
+      static const bool generic_only = []() { const char* e = getenv("LYCO_MERGE_GENERIC"); return e && *e == '1'; }();
+      const bool f32_bf16 = !generic_only && d->f_dtype == LYCO_F32 && d->w_dtype == LYCO_BF16 && !d->pre_round;
+      const bool all_bf16 = !generic_only && d->f_dtype == LYCO_BF16 && d->w_dtype == LYCO_BF16 && d->pre_round &&
+                            d->pre_dtype == LYCO_BF16;
+      if (vec && f32_bf16)
+        lyco::merge_lokr_kernel<8, LYCO_F32, LYCO_BF16, lyco::PD_NONE><<<grid, 256, 0, stream>>>(*d, w, wo);
+      else if (vec && all_bf16)
+        lyco::merge_lokr_kernel<8, LYCO_BF16, LYCO_BF16, LYCO_BF16><<<grid, 256, 0, stream>>>(*d, w, wo);
+      else if (vec) lyco::merge_lokr_kernel<8><<<grid, 256, 0, stream>>>(*d, w, wo);
       else lyco::merge_lokr_kernel<1><<<grid, 256, 0, stream>>>(*d, w, wo);
       break;
     }
@@ -683,7 +693,12 @@ int lyco_merge_weight(const lyco_delta_desc_t* d, const void* W, void* W_out, vo
       int grid = static_cast<int>((total / 8 + 255) / 256);
       const int cap = di.sms * 16;
       if (grid > cap) grid = cap;
-      lyco::merge_raw_kernel<<<grid, 256, 0, stream>>>(*d, w, wo);
+      static const bool generic_only = []() { const char* e = getenv("LYCO_MERGE_GENERIC"); return e && *e == '1'; }();
+      if (!generic_only && d->f_dtype == LYCO_BF16 && d->w_dtype == LYCO_BF16 && d->pre_round &&
+          d->pre_dtype == LYCO_BF16)
+        lyco::merge_raw_kernel<LYCO_BF16><<<grid, 256, 0, stream>>>(*d, w, wo);
+      else
+        lyco::merge_raw_kernel<><<<grid, 256, 0, stream>>>(*d, w, wo);
       break;
     }
   }

@@ -174,14 +174,27 @@ __global__ void __launch_bounds__(256) merge_lowrank_kernel(lyco_delta_desc_t d,
   }
 }
 
+// Compile-time dtype specialisation for the one-pass merge kernels.  FD / WD = factor / weight dtype, PD = the
+// product domain: PD_RUNTIME -> everything read from the descriptor (generic instantiation), PD_NONE -> no
+// pre-rounding (fp32 product), otherwise pre_round with that dtype.  The kernel source is the SAME for every
+// instantiation — the local constants below replace the descriptor fields, the compiler folds the dtype switches of
+// rnd / ld_f / cvt16 / to16 — so a specialised kernel computes bit for bit what the generic one does.
+constexpr int DT_RUNTIME = -1;
+constexpr int PD_RUNTIME = -2;
+constexpr int PD_NONE = -1;
+
 // LoKr: dW[pu*vp+pv, u*vq+v] = w1[pu,u] * w2[pv,v]   (functional/lokr.py:11-20 via torch.kron)
-template <int VEC>
+template <int VEC, int FD = DT_RUNTIME, int WD = DT_RUNTIME, int PD = PD_RUNTIME>
 __global__ void __launch_bounds__(256) merge_lokr_kernel(lyco_delta_desc_t d, const uint16_t* __restrict__ W,
                                                          uint16_t* __restrict__ Wout) {
+  const int f_dtype = FD == DT_RUNTIME ? d.f_dtype : FD;
+  const int w_dtype = WD == DT_RUNTIME ? d.w_dtype : WD;
+  const int pre_round = PD == PD_RUNTIME ? d.pre_round : (PD == PD_NONE ? 0 : 1);
+  const int pre_dtype = PD == PD_RUNTIME ? d.pre_dtype : (PD == PD_NONE ? LYCO_F32 : PD);
   const int K = d.in_dim;
   const int64_t total = static_cast<int64_t>(d.out_dim) * K / VEC;
-  const Chain ch{d.pre_round, d.pre_dtype, d.w_dtype, d.m_pre, d.m_post1, d.m_post2};
-  const int fround = d.pre_round ? d.pre_dtype : LYCO_F32;
+  const Chain ch{pre_round, pre_dtype, w_dtype, d.m_pre, d.m_post1, d.m_post2};
+  const int fround = pre_round ? pre_dtype : LYCO_F32;
   const int kv = K / VEC;
   for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
        idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -189,7 +202,7 @@ __global__ void __launch_bounds__(256) merge_lokr_kernel(lyco_delta_desc_t d, co
     const int k = static_cast<int>(idx % kv) * VEC;
     const int pu = n / d.vp, pv = n % d.vp;
     const int u = k / d.vq, v = k % d.vq;  // VEC divides vq -> the vector stays inside one w1 block
-    const float a = rnd(ld_f(d.f0, d.f_dtype, pu * d.uq + u), fround);
+    const float a = rnd(ld_f(d.f0, f_dtype, pu * d.uq + u), fround);
     const int64_t off = static_cast<int64_t>(n) * K + k;
     if (VEC == 8) {
       const uint4 wv = __ldg(reinterpret_cast<const uint4*>(W + off));
@@ -198,24 +211,29 @@ __global__ void __launch_bounds__(256) merge_lokr_kernel(lyco_delta_desc_t d, co
       uint16_t* oh = reinterpret_cast<uint16_t*>(&ov);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float b = rnd(ld_f(d.f1, d.f_dtype, static_cast<int64_t>(pv) * d.vq + v + j), fround);
-        oh[j] = to16(merged(cvt16(wh[j], d.w_dtype), apply_chain(a * b, ch), d.w_dtype), d.w_dtype);
+        const float b = rnd(ld_f(d.f1, f_dtype, static_cast<int64_t>(pv) * d.vq + v + j), fround);
+        oh[j] = to16(merged(cvt16(wh[j], w_dtype), apply_chain(a * b, ch), w_dtype), w_dtype);
       }
       *reinterpret_cast<uint4*>(Wout + off) = ov;
     } else {
-      const float b = rnd(ld_f(d.f1, d.f_dtype, static_cast<int64_t>(pv) * d.vq + v), fround);
-      Wout[off] = to16(merged(cvt16(W[off], d.w_dtype), apply_chain(a * b, ch), d.w_dtype), d.w_dtype);
+      const float b = rnd(ld_f(d.f1, f_dtype, static_cast<int64_t>(pv) * d.vq + v), fround);
+      Wout[off] = to16(merged(cvt16(W[off], w_dtype), apply_chain(a * b, ch), w_dtype), w_dtype);
     }
   }
 }
 
 // RAW: the rank-r products were formed on the tensor cores (lyco_gemm with K = r) and arrive as 16-bit
 // [N, K'] arrays: W' = rnd(W + chain(raw1 [* raw2])).  Used for LoCon / DyLoRA (one product) and LoHa (two).
+// D16 != DT_RUNTIME: products, product domain and weights all in that 16-bit dtype (the autocast / all-bf16 regimes).
+template <int D16 = DT_RUNTIME>
 __global__ void __launch_bounds__(256) merge_raw_kernel(lyco_delta_desc_t d, const uint16_t* __restrict__ W,
                                                         uint16_t* __restrict__ Wout) {
+  const int w_dtype = D16 == DT_RUNTIME ? d.w_dtype : D16;
+  const int pre_round = D16 == DT_RUNTIME ? d.pre_round : 1;
+  const int pre_dtype = D16 == DT_RUNTIME ? d.pre_dtype : D16;
+  const int pd = D16 == DT_RUNTIME ? d.f_dtype : D16;  // dtype of the raw products
   const int64_t total8 = static_cast<int64_t>(d.out_dim) * d.in_dim / 8;
-  const Chain ch{d.pre_round, d.pre_dtype, d.w_dtype, d.m_pre, d.m_post1, d.m_post2};
-  const int pd = d.f_dtype;  // dtype of the raw products
+  const Chain ch{pre_round, pre_dtype, w_dtype, d.m_pre, d.m_post1, d.m_post2};
   const uint4* r1 = reinterpret_cast<const uint4*>(d.f0);
   const uint4* r2 = reinterpret_cast<const uint4*>(d.f1);
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total8;
@@ -233,7 +251,7 @@ __global__ void __launch_bounds__(256) merge_raw_kernel(lyco_delta_desc_t d, con
     for (int j = 0; j < 8; ++j) {
       float raw = cvt16(ah[j], pd);
       if (r2) raw *= cvt16(bh[j], pd);
-      oh[j] = to16(merged(cvt16(wh[j], d.w_dtype), apply_chain(raw, ch), d.w_dtype), d.w_dtype);
+      oh[j] = to16(merged(cvt16(wh[j], w_dtype), apply_chain(raw, ch), w_dtype), w_dtype);
     }
     reinterpret_cast<uint4*>(Wout)[i] = ov;
   }
@@ -410,30 +428,38 @@ __global__ void __launch_bounds__(256) grad_lokr_kernel(lyco_delta_desc_t d, con
   }
   const int lane = threadIdx.x & 31;
   const float* row = dW + static_cast<int64_t>(pu * d.vp + pv) * K + v;
-  for (int u = 0; u < d.uq; ++u) {
-    float g[VEC];
-    if (live) {
+  // Groups of four w1 columns: the four (read-only) row loads of a group are issued before the first shuffle tree, so
+  // a thread keeps 64 bytes in flight instead of 16.  Per-u arithmetic and its order are unchanged.
+  constexpr int UG = 4;
+  for (int u0 = 0; u0 < d.uq; u0 += UG) {
+    float g[UG][VEC];
+#pragma unroll
+    for (int j = 0; j < UG; ++j) {
+      const bool on = live && (u0 + j < d.uq);
       if (VEC == 4) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(row + static_cast<int64_t>(u) * d.vq));
-        g[0] = t.x; g[1 % VEC] = t.y; g[2 % VEC] = t.z; g[3 % VEC] = t.w;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (on) t = __ldg(reinterpret_cast<const float4*>(row + static_cast<int64_t>(u0 + j) * d.vq));
+        g[j][0] = t.x; g[j][1 % VEC] = t.y; g[j][2 % VEC] = t.z; g[j][3 % VEC] = t.w;
       } else {
-        g[0] = __ldg(row + static_cast<int64_t>(u) * d.vq);
+        g[j][0] = on ? __ldg(row + static_cast<int64_t>(u0 + j) * d.vq) : 0.f;
       }
-    } else {
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) g[i] = 0.f;
-    }
-    const float a = rnd(ld_f(d.f0, d.f_dtype, pu * d.uq + u), fround);
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      g[i] *= gscale;
-      acc[i] = fmaf(a, g[i], acc[i]);
-      s = fmaf(g[i], b[i], s);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) atomicAdd(&s_w1[u], s);
+    for (int j = 0; j < UG; ++j) {
+      const int u = u0 + j;
+      if (u >= d.uq) break;  // warp-uniform
+      const float a = rnd(ld_f(d.f0, d.f_dtype, pu * d.uq + u), fround);
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const float gi = g[j][i] * gscale;
+        acc[i] = fmaf(a, gi, acc[i]);
+        s = fmaf(gi, b[i], s);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) atomicAdd(&s_w1[u], s);
+    }
   }
   if (live) {
 #pragma unroll
