@@ -1,22 +1,28 @@
 #!/usr/bin/env python
-"""bench.py — SDXL-UNet + LoKr (factor 8, full-dim) fwd+bwd step rate on N x B200.
+"""bench.py — LyCORIS adapter fwd+bwd step rate on N x B200 (default: SDXL-UNet + LoKr factor 8 full-dim).
 
-    python bench.py --gpus N --steps K --warmup W          # this engine (default arm)
-    python bench.py --impl reference ...                   # the reference's CPU path (oracle port)
-    python bench.py --impl reference-gpu ...               # informational: reference-equivalent eager ATen path on the GPU
+    python bench.py --gpus N --steps K --warmup W              # this engine (default arm), BASELINE cfg #4
+    python bench.py --config cfg2|cfg3|cfg4|cfg5 ...           # the other BASELINE.json configs
+    python bench.py --impl reference ...                       # the reference's own CPU path on the host cores
+    python bench.py --impl reference-gpu ...                   # the UNMODIFIED reference, PyTorch-eager, on one GPU
 
-Workload (BASELINE.json configs[3]): SDXL-shaped UNet (788 wrapped layers,
-F1 = 47.81 TFLOP per dense pass at batch 8), bf16 base weights, fp32 adapter parameters under
-torch.autocast(bf16) (the kohya regime), LoKr factor 8 full-dim (network_dim 100000) via
-lycoris_b200.kohya.create_network, preset "full", per-GPU batch 8, 1024x1024 (latents 128x128),
-synthetic N(0,1) latents/context, MSE loss in fp32.  A step is forward + backward (+ the NCCL
-adapter-gradient all-reduce when N > 1); there is no optimizer step in the metric.
+Workloads (BASELINE.json configs): SDXL- / SD1.5-shaped UNet skeleton, bf16 base weights, fp32
+adapter parameters under torch.autocast(bf16) (the kohya regime), adapters created through
+``<package>.kohya.create_network`` exactly as kohya sd-scripts does, synthetic N(0,1) latents / context,
+MSE loss in fp32.  A step is forward + backward (+ the NCCL adapter-gradient all-reduce, overlapped with
+backward, when N > 1); there is no optimizer step in the metric.
+
+The engine arm at N = 1 also times, in the same process and on the same model / parameters / inputs, the
+unmodified reference from baseline/_ref through ITS public API (``lycoris.kohya``), PyTorch-eager — the
+denominator BASELINE.json's >=4x target names — cross-checks the two losses, and times the reference's CPU
+path on the host cores on a bounded sample (``cpu_baseline``).
 
 Prints ONE JSON line (rank 0).
 """
 import argparse
 import json
 import os
+import statistics
 import subprocess
 import sys
 import threading
@@ -24,6 +30,24 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+CFG5_PRESET = os.path.join(ROOT, "workloads", "cfg5_mixed_preset.toml")
+
+# BASELINE.json configs[1..4]; per-GPU batch except cfg5 whose batch 16 is GLOBAL (split over the ranks)
+CONFIGS = {
+    "cfg2": dict(model="sd15", batch=4, label="LoCon", note="dim 16 conv_dim 8 alpha 8",
+                 dim=16, alpha=8, kw=dict(algo="locon", conv_dim=8, conv_alpha=8, preset="full")),
+    "cfg3": dict(model="sdxl", batch=8, label="LoHa", note="dim 32 conv_dim 16",
+                 dim=32, alpha=16, kw=dict(algo="loha", conv_dim=16, conv_alpha=8, preset="full")),
+    "cfg4": dict(model="sdxl", batch=8, label="LoKr", note="factor 8, full-dim",
+                 dim=100000, alpha=1, kw=dict(algo="lokr", factor=8, preset="full")),
+    "cfg5": dict(model="sdxl", batch=16, global_batch=True, label="mixed(LoCon+LoHa+LoKr+IA3)",
+                 note="locon d16/c8 on ResnetBlock2D + samplers, lokr f8 full on FeedForward, loha d16 on attention "
+                      "q/out + proj, ia3 on to_k/to_v (workloads/cfg5_mixed_preset.toml)",
+                 dim=16, alpha=8, kw=dict(algo="locon", conv_dim=8, conv_alpha=4, preset=CFG5_PRESET)),
+}
+ALGO_TO_CFG = {"lokr": "cfg4", "loha": "cfg3", "locon": "cfg2"}
 
 
 def parse():
@@ -32,16 +56,36 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference", "reference-gpu"])
-    ap.add_argument("--batch", type=int, default=8, help="per-GPU batch")
-    ap.add_argument("--model", default="sdxl", choices=["sdxl", "sd15", "toy"])
-    ap.add_argument("--algo", default="lokr")
+    ap.add_argument("--config", default="", choices=["", "cfg2", "cfg3", "cfg4", "cfg5"],
+                    help="BASELINE.json config (default cfg4 = SDXL + LoKr f8 full-dim, per-GPU batch 8)")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
+    ap.add_argument("--model", default="", choices=["", "sdxl", "sd15", "toy"], help="model override")
+    ap.add_argument("--algo", default="", help="shorthand: lokr|loha|locon pick the adapter of cfg4|cfg3|cfg2")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of a CUDA graph")
     ap.add_argument("--sample-size", type=int, default=0, help="latent side (default: the model's)")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-gpu-reference", action="store_true", help="do not time the unmodified reference on the GPU")
+    ap.add_argument("--ref-steps", type=int, default=20, help="timed steps of the GPU-eager reference leg")
     ap.add_argument("--kernel-table", default="", help="write a per-kernel CUDA-time table of one eager step here")
     ap.add_argument("--nvtx-step", action="store_true", help="wrap ONE extra eager step in an NVTX range 'lyco_step' (for ncu --nvtx-include)")
-    return ap.parse_args()
+    args = ap.parse_args()
+    name = args.config or ALGO_TO_CFG.get(args.algo, "cfg4")
+    wl = dict(CONFIGS[name])
+    wl["name"] = name
+    if args.algo and not args.config:
+        # --algo on the default model: the adapter settings of that config on the SDXL model (round-1 behaviour)
+        wl["model"], wl["batch"] = "sdxl", 8
+    if args.model:
+        wl["model"] = args.model
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.batch:
+        wl["batch"] = args.batch
+        wl["global_batch"] = False
+    elif wl.get("global_batch"):
+        wl["batch"] = max(1, wl["batch"] // world)
+    args.wl = wl
+    return args
 
 
 # ------------------------------------------------------------------------------ clocks
@@ -99,21 +143,6 @@ def model_cfg(name):
     return {"sdxl": SDXL, "sd15": SD15, "toy": TOY}[name]
 
 
-def network_args(algo):
-    if algo == "lokr":
-        return dict(network_dim=100000, network_alpha=1, kw=dict(algo="lokr", factor=8, preset="full"))
-    if algo == "locon":
-        return dict(network_dim=16, network_alpha=8, kw=dict(algo="locon", conv_dim=8, conv_alpha=8, preset="full"))
-    if algo == "loha":
-        return dict(network_dim=32, network_alpha=16, kw=dict(algo="loha", conv_dim=16, conv_alpha=8, preset="full"))
-    raise KeyError(algo)
-
-
-NCU_TRAFFIC_DOMINANT = 183.3e6  # bytes per launch (52.8 MB read + 130.5 MB written), see profiles/
-
-ALGO_NOTE = {"lokr": "factor 8, full-dim", "locon": "dim 16 conv_dim 8 alpha 8", "loha": "dim 32 conv_dim 16"}
-
-
 def perturb_zero_factors(net, seed=1):
     import torch
 
@@ -124,32 +153,107 @@ def perturb_zero_factors(net, seed=1):
                 p.copy_((torch.randn(p.shape, generator=g) * 0.01).to(p.device, p.dtype))
 
 
+def create_network(kohya_mod, wl, unet):
+    """The call kohya sd-scripts makes: ``network_module.create_network(multiplier, dim, alpha, vae, te, unet, **kw)``."""
+    import torch
+
+    torch.manual_seed(1)
+    return kohya_mod.create_network(1.0, wl["dim"], wl["alpha"], None, None, unet, **wl["kw"])
+
+
+def import_reference():
+    """The UNMODIFIED reference package vendored by ``__graft_entry__.build()`` (pip install --target
+    baseline/_ref).  Returns (lycoris.kohya module, notes) or (None, why)."""
+    if not os.path.isdir(os.path.join(REF_DIR, "lycoris")):
+        return None, "baseline/_ref is empty (run __graft_entry__.build() where /root/reference exists)"
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    try:
+        import lycoris.kohya as ref_kohya
+        import lycoris.wrapper as ref_wrapper
+        from lycoris.modules.ia3 import IA3Module
+    except Exception as e:  # noqa: BLE001
+        return None, f"import failed: {type(e).__name__}: {e}"
+    notes = []
+    if "ia3" not in ref_wrapper.network_module_dict:
+        # upstream omission (lycoris/wrapper.py:45-55): the class exists but is not registered, so any preset that
+        # names algo="ia3" raises KeyError.  Registering the reference's OWN class is the one change made.
+        ref_wrapper.network_module_dict["ia3"] = IA3Module
+        notes.append("registered the reference's own IA3Module under 'ia3' in network_module_dict (upstream omission)")
+    return ref_kohya, notes
+
+
 def build_engine_workload(args, device):
     import torch
 
     import lycoris_b200.kohya as kohya
     from workloads.unet_skeleton import UNetSkeleton, wrapped_layer_flops
 
-    cfg = model_cfg(args.model)
+    wl = args.wl
+    cfg = model_cfg(wl["model"])
     torch.manual_seed(0)
     # activations travel channels_last (NHWC) — what the TMA-im2col producer and cuDNN both want; the
     # frozen filters stay in PyTorch's [O, C, kh, kw] layout, which is the layout the reference flattens
     unet = UNetSkeleton(cfg).to(device=device, dtype=torch.bfloat16)
     unet.requires_grad_(False)
     unet.train()
-    na = network_args(args.algo)
-    torch.manual_seed(1)
-    net = kohya.create_network(1.0, na["network_dim"], na["network_alpha"], None, None, unet, **na["kw"])
+    net = create_network(kohya, wl, unet)
     net.apply_to(None, unet, False, True)
     net.to(device)
     perturb_zero_factors(net, 1)
     net.requires_grad_(True)
     net.train()
-    f1, n_layers = wrapped_layer_flops(unet, args.batch, args.sample_size or None)
+    f1, n_layers = wrapped_layer_flops(unet, wl["batch"], args.sample_size or None)
     return unet, net, f1, n_layers
 
 
-def make_step(unet, net, static, dp):
+def algorithmic_flops(net, rows_of):
+    """F_alg = sum over wrapped layers of c * 2*M*N*K' + F_side, c = 2 (LoCon, LoKr, IA3, DyLoRA)
+    or 3 (LoHa); F_side: LoCon 3*2*M*r*(N+K'), LoKr 3*2*M*(uq*vq*vp + vp*uq*up), LoHa 8*2*N*K'*r."""
+    total = 0.0
+    for lora in net.loras:
+        M = rows_of.get(lora.lora_name)
+        if M is None:
+            continue
+        N = lora.shape[0]
+        Kp = 1
+        for s in lora.shape[1:]:
+            Kp *= s
+        kind = type(lora).__name__
+        dense = 2.0 * M * N * Kp
+        if kind == "LohaModule":
+            total += 3 * dense + 8 * 2.0 * N * Kp * lora.lora_dim
+        elif kind == "LokrModule":
+            w1 = lora.lokr_w1 if lora.use_w1 else None
+            up, uq = (w1.shape if w1 is not None else (lora.lokr_w1_a.shape[0], lora.lokr_w1_b.shape[1]))
+            vp, vq = N // up, Kp // uq
+            total += 2 * dense + 3 * 2.0 * M * (uq * vq * vp + vp * uq * up)
+        elif kind in ("LoConModule", "DyLoraModule"):
+            total += 2 * dense + 3 * 2.0 * M * lora.lora_dim * (N + Kp)
+        else:
+            total += 2 * dense
+    return total
+
+
+def layer_rows(unet, net, batch, sample_size=None):
+    """{lora_name: M} — rows (batch x positions / tokens) each wrapped layer contracts over, from a no-grad
+    forward with hooks on the base layers (run BEFORE timing; the tensors are tiny bookkeeping)."""
+    import torch
+
+    rows = {}
+    hooks = []
+    for lora in net.loras:
+        org = lora.org_module[0]
+
+        def hook(m, inp, out, _n=lora.lora_name):
+            o = out
+            rows[_n] = o.numel() // o.shape[1] if o.dim() == 4 else o.numel() // o.shape[-1]
+
+        hooks.append(org.register_forward_hook(hook))
+    return rows, hooks
+
+
+def make_step(unet, net, static, dp, comm=True):
     import torch
     import torch.nn.functional as F
 
@@ -163,9 +267,28 @@ def make_step(unet, net, static, dp):
             out = unet(static["sample"], static["timesteps"], static["context"], static.get("added_cond"))
         loss = F.mse_loss(out.float(), static["target"].float())
         loss.backward()
+        if dp is not None and comm:
+            dp.allreduce()  # buckets not yet issued from inside backward
+            dp.wait()       # join the comm stream (inside the captured graph)
         return loss
 
     return step
+
+
+def ncu_traffic(wl_name):
+    """dram bytes per launch of the dominant kernel from a COMMITTED ncu capture (profiles/*traffic*.json written by
+    tools/ncu_summarize.py); None when no capture for this workload is committed."""
+    import glob
+
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_traffic_*.json"))):
+        try:
+            rec = json.load(open(path))
+        except Exception:  # noqa: BLE001
+            continue
+        if rec.get("workload", "cfg4") == wl_name:
+            best = dict(rec, file=os.path.relpath(path, ROOT))
+    return best
 
 
 def run_engine(args):
@@ -176,6 +299,7 @@ def run_engine(args):
     from lycoris_b200.engine import kernels as K
     from lycoris_b200.engine.ddp import FlatGradAllReduce
 
+    wl = args.wl
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -191,10 +315,13 @@ def run_engine(args):
 
     unet, net, f1, n_layers = build_engine_workload(args, device)
     n_params = sum(p.numel() for p in net.parameters())
-    dp = FlatGradAllReduce(list(net.parameters()), overlap=True) if world > 1 else None
+    algo_table = {}
+    for lora in net.loras:
+        algo_table[type(lora).__name__] = algo_table.get(type(lora).__name__, 0) + 1
+    dp = FlatGradAllReduce(list(net.parameters()), overlap="backward") if world > 1 else None
 
     cfg = unet.cfg
-    host = unet.synthetic_batch(args.batch, "cpu", torch.bfloat16, seed=2 + rank, sample_size=args.sample_size or None)
+    host = unet.synthetic_batch(wl["batch"], "cpu", torch.bfloat16, seed=2 + rank, sample_size=args.sample_size or None)
     host = {k: (v.to(torch.bfloat16) if v.is_floating_point() else v).pin_memory() for k, v in host.items()}
     static = {}
     for k, v in host.items():
@@ -207,45 +334,44 @@ def run_engine(args):
 
     # warm-up (eager) — also primes cuDNN heuristics, TMA descriptors, cached host scalars
     torch.cuda.synchronize()
-    for _ in range(max(args.warmup, 3)):
+    rows_of, hooks = layer_rows(unet, net, wl["batch"])
+    loss = step()
+    for h in hooks:
+        h.remove()
+    for _ in range(max(args.warmup, 3) - 1):
         loss = step()
-        if dp is not None:
-            dp.allreduce()
-            dp.wait()
     torch.cuda.synchronize()
+    f_alg = algorithmic_flops(net, rows_of)
 
-    graph = None
-    static_loss = None
-    if not args.no_graph:
+    def capture(fn):
         try:
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                static_loss = step()
-            graph.replay()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = fn()
+            g.replay()
             torch.cuda.synchronize()
+            return g, out
         except Exception as e:  # noqa: BLE001
             if rank == 0:
                 print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); running eager", file=sys.stderr)
-            graph = None
             torch.cuda.synchronize()
+            return None, None
+
+    graph, static_loss = (None, None) if args.no_graph else capture(step)
 
     def one_step():
         if graph is not None:
             graph.replay()
-            out = static_loss
-        else:
-            out = step()
-        if dp is not None:
-            dp.allreduce()
-            dp.wait()
-        return out
+            return static_loss
+        return step()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(n, e2e):
+    def timed(n, e2e, fn=None):
+        fn = fn or one_step
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
@@ -254,9 +380,9 @@ def run_engine(args):
             if e2e:
                 for k, v in host.items():
                     static[k].copy_(v, non_blocking=True)
-                last = float(one_step().detach())  # device -> host read of the step's result
+                last = float(fn().detach())  # device -> host read of the step's result
             else:
-                last = one_step()
+                last = fn()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -268,14 +394,25 @@ def run_engine(args):
 
     for _ in range(args.warmup):
         one_step()
-    launches0 = _lib.launch_count()
     with ClockSampler(local_rank) as clocks:
         ms_step, _ = timed(args.steps, e2e=False)
         ms_e2e, loss_val = timed(args.steps, e2e=True)
-    launches = _lib.launch_count() - launches0
-    if graph is not None:
-        # graph replays do not pass through the C-ABI; count the launches of one captured step instead
-        launches = None
+
+    # exposed communication: the same step captured WITHOUT the collective, timed the same way (fewer steps)
+    allreduce_exposed_ms = None
+    buckets_overlapped = None
+    if dp is not None:
+        buckets_overlapped = [dp.buckets_overlapped, len(dp.buckets)]
+        dp._armed = False
+        step_nc = make_step(unet, net, static, dp, comm=False)
+        g_nc, loss_nc = (None, None) if args.no_graph else capture(step_nc)
+        fn_nc = (lambda: (g_nc.replay(), loss_nc)[1]) if g_nc is not None else step_nc
+        for _ in range(2):
+            fn_nc()
+        ms_nc, _ = timed(max(3, min(args.steps, 8)), e2e=False, fn=fn_nc)
+        allreduce_exposed_ms = ms_step - ms_nc
+        del g_nc
+        step = step_nc  # the instrumented eager steps below run without the collective (rank-local)
 
     # instrumented eager steps: CUDA-event pair around every lyco_gemm launch (same stream)
     sink = []
@@ -310,70 +447,9 @@ def run_engine(args):
     eager_ms = e0.elapsed_time(e1)
 
     gemm_kernel_ms = None
+    kernel_ms = {}
     if rank == 0:
-        from torch.profiler import ProfilerActivity, profile, record_function
-
-        from lycoris_b200.engine import ops as _ops
-
-        def _labelled(fn, label):
-            def wrapped(*a, **k):
-                with record_function(label):
-                    return fn(*a, **k)
-            return staticmethod(wrapped)
-
-        saved = {}
-        for cls in (_ops._AdapterContraction, _ops._MergedContraction):
-            saved[cls] = (cls.forward, cls.backward)
-            cls.forward = _labelled(cls.forward, "lyco_node_fwd")
-            cls.backward = _labelled(cls.backward, "lyco_node_bwd")
-        try:
-            with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
-                step()
-                torch.cuda.synchronize()
-        finally:
-            for cls, (f, b) in saved.items():
-                cls.forward, cls.backward = staticmethod(f), staticmethod(b)
-        # attribute every kernel to "inside an engine autograd node" or "model side" via the CPU op that launched it
-        inside, outside = {}, {}
-        for ev in prof.events():
-            ks = getattr(ev, "kernels", None)
-            if not ks:
-                continue
-            anc, tag = ev, None
-            while anc is not None:
-                if anc.name in ("lyco_node_fwd", "lyco_node_bwd"):
-                    tag = anc.name
-                    break
-                anc = anc.cpu_parent
-            for k in ks:
-                name = k.name.split("<")[0][:70]
-                dst = inside if tag else outside
-                a = dst.setdefault(name, [0, 0.0])
-                a[0] += 1
-                a[1] += k.duration
-        if args.kernel_table:
-            with open(args.kernel_table + ".attribution", "w") as fh:
-                for title, d in (("launched inside the engine's autograd nodes", inside),
-                                 ("model side (outside)", outside)):
-                    tot_d = sum(v[1] for v in d.values())
-                    fh.write(f"{title}: {tot_d / 1e3:.2f} ms\n")
-                    for name, (cnt, t) in sorted(d.items(), key=lambda kv: -kv[1][1])[:14]:
-                        fh.write(f"{t / 1e3:10.3f} ms {cnt:6d}  {name}\n")
-        agg = {}
-        for ev in prof.events():
-            if (ev.device_type is not None and str(ev.device_type).endswith("CUDA") and ev.device_time_total > 0
-                    and not ev.name.startswith("lyco_node_")):
-                name = ev.name.split("<")[0][:90]
-                a = agg.setdefault(name, [0, 0.0])
-                a[0] += 1
-                a[1] += ev.device_time_total
-        tot = sum(v[1] for v in agg.values())
-        gemm_kernel_ms = sum(v[1] for k, v in agg.items() if "gemm_sm100_kernel" in k) / 1e3
-        if args.kernel_table:
-            with open(args.kernel_table, "w") as fh:
-                fh.write(f"one eager step, CUDA kernels by total device time (us); sum = {tot / 1e3:.2f} ms\n")
-                for name, (cnt, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-                    fh.write(f"{t / 1e3:10.3f} ms {100 * t / tot:5.1f}% {cnt:6d}  {name}\n")
+        gemm_kernel_ms, kernel_ms = profile_one_step(args, step)
     if args.nvtx_step:
         # start/end (not push/pop) ranges are process-wide: backward kernels are launched from autograd's
         # worker thread and would fall outside a thread-local push/pop range
@@ -396,8 +472,9 @@ def run_engine(args):
             dist.destroy_process_group()
         return
     steps_per_s = world * 1000.0 / ms_step
+    traffic = ncu_traffic(wl["name"])
     result = {
-        "metric": f"SDXL-UNet+{ {'lokr': 'LoKr', 'locon': 'LoCon', 'loha': 'LoHa'}[args.algo] } fwd+bwd steps/sec",
+        "metric": f"{cfg.name.upper()}-UNet+{wl['label']} fwd+bwd steps/sec",
         "value": steps_per_s,
         "unit": "steps/s",
         "n_gpus": world,
@@ -405,18 +482,19 @@ def run_engine(args):
         "warmup": args.warmup,
         "ms_per_step": ms_step,
         "higher_is_better": True,
-        "scaling": "weak",
+        "scaling": "strong" if wl.get("global_batch") else "weak",
         "vs_baseline": None,
         "dtype": "bf16",
         "data": "synthetic",
         "impl": "engine",
         "config": {
-            "workload": f"{cfg.name}-unet-skeleton + {args.algo} ({ALGO_NOTE[args.algo]}) via lycoris_b200.kohya, preset full, "
-                        f"per-GPU batch {args.batch}, latents {args.sample_size or cfg.sample_size}^2, fwd+bwd, "
-                        "bf16 base / fp32 adapter / autocast",
+            "workload": f"{wl['name']}: {cfg.name}-unet-skeleton + {wl['label']} ({wl['note']}) via lycoris_b200.kohya."
+                        f"create_network, per-GPU batch {wl['batch']}, latents {args.sample_size or cfg.sample_size}^2, "
+                        "fwd+bwd, bf16 base / fp32 adapter / autocast",
             "wrapped_layers": n_layers,
+            "adapters": algo_table,
             "adapter_params": n_params,
-            "global_batch": args.batch * world,
+            "global_batch": wl["batch"] * world,
             "parallelism": f"dp{world}",
             "cuda_graph": graph is not None,
             "l2": "inputs+weights+activations per step (>10 GB) exceed the 126 MB L2",
@@ -429,235 +507,426 @@ def run_engine(args):
         "gpu_launches": per_step_launches * args.steps * 2,
         "lyco_launches_per_step": per_step_launches,
         "roofline": {
-            "bound": "tensor", "kernel": "gemm_sm100_kernel (fwd / dgrad / wgrad of the wrapped Linear layers)",
+            "bound": "tensor", "kernel": "gemm_sm100_kernel (fwd / dgrad / wgrad contractions of the wrapped Linear layers)",
             "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-            "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1400",
-            # dram__bytes_read+write per launch of the step's dominant GEMM (GEGLU proj forward, M=8192 N=10240
-            # K=1280) from the committed `ncu --set full` capture profiles/r01_ncu_full_summary.txt
-            "traffic": NCU_TRAFFIC_DOMINANT if args.model == "sdxl" else None,
-            "traffic_shape": "M=8192 N=10240 K=1280 fwd: algorithmic 2*(MK+NK+MN) = 215.0e6 B" if args.model == "sdxl" else None,
-            "gemm_launches_per_step": len(sink), "gemm_ms_per_step": gemm_ms, "gemm_share_of_eager_step": gemm_ms / eager_ms, "eager_step_ms_gpu_bound": eager_ms,
-            "algorithmic_tflop_per_step": gemm_flops / 1e12,
-            # the event brackets above also contain the wgrad memsets and ~5 us of stream front-end gap per launch;
+            "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1400 (of fallback)",
+            # dram__bytes_read+write per launch of the dominant GEMM from a committed `ncu --set full` capture
+            "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+            "traffic_source": traffic,
+            "gemm_launches_per_step": len(sink), "gemm_ms_per_step": gemm_ms, "gemm_share_of_eager_step": gemm_ms / eager_ms,
+            "eager_step_ms_gpu_bound": eager_ms,
+            # FLOPs the GEMM launches EXECUTE (every contraction the engine runs, structured or dense)
+            "executed_tflop_per_step": gemm_flops / 1e12,
+            # the event brackets above also contain the split-K memsets and the stream front-end gap per launch;
             # the same launches by CUPTI kernel duration (torch.profiler over one eager step):
             "gemm_kernel_ms_per_step_cupti": gemm_kernel_ms,
             "achieved_cupti": (gemm_flops / (gemm_kernel_ms * 1e-3) / 1e12) if gemm_kernel_ms else None,
+            # ALGORITHMIC work of the adapter path (c*F1 + F_side, c = 2 or 3 — never the
+            # reference's redundant 5*F1) over the WHOLE step time, model-side ops included
+            "algorithmic": {
+                "tflop_per_step": f_alg / 1e12, "tflops": f_alg / (ms_step * 1e-3) / 1e12,
+                "frac_of_peak": f_alg / (ms_step * 1e-3) / 1e12 / peak_tf,
+                "note": "F_alg / whole-step time; the step also holds attention, norms and elementwise ops of the model",
+            },
+            "engine_kernel_ms_per_step_cupti": kernel_ms,
         },
         "clocks": clocks.summary(),
     }
+    if dp is not None:
+        result["allreduce_exposed_ms"] = allreduce_exposed_ms
+        result["allreduce"] = {"buckets_issued_inside_backward": buckets_overlapped[0], "buckets": buckets_overlapped[1],
+                               "elements": dp.num_elements, "mode": dp.mode}
+    if world == 1 and not args.skip_gpu_reference:
+        del graph
+        graph = None
+        torch.cuda.synchronize()
+        result["gpu_eager_reference"] = gpu_eager_reference(args, unet, net, static, loss_val)
+        ref = result["gpu_eager_reference"]
+        if ref.get("ms_per_step"):
+            result["speedup_vs_gpu_eager"] = ref["ms_per_step"] / ms_step
     if not args.skip_cpu_baseline and world == 1:
-        result["cpu_baseline"] = cpu_reference(args, budget_s=args.cpu_seconds)
+        result["cpu_baseline"] = cpu_reference(args, budget_s=args.cpu_seconds, reps=3)
     print(json.dumps(result), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-# ------------------------------------------------------------------ reference arms
-def distinct_wrapped_shapes(args):
-    """[(kind, N, K, ksize, stride, M_per_sample_or_tokens, count)] of the wrapped layers."""
+def profile_one_step(args, step):
+    """torch.profiler (CUPTI) over one eager step: GEMM kernel time, per-engine-kernel totals, optional tables."""
+    import torch
+    from torch.profiler import ProfilerActivity, profile, record_function
+
+    from lycoris_b200.engine import ops as _ops
+
+    def _labelled(fn, label):
+        def wrapped(*a, **k):
+            with record_function(label):
+                return fn(*a, **k)
+        return staticmethod(wrapped)
+
+    saved = {}
+    node_classes = [c for c in vars(_ops).values() if isinstance(c, type) and issubclass(c, torch.autograd.Function)
+                    and c is not torch.autograd.Function]
+    for cls in node_classes:
+        saved[cls] = (cls.forward, cls.backward)
+        cls.forward = _labelled(cls.forward, "lyco_node_fwd")
+        cls.backward = _labelled(cls.backward, "lyco_node_bwd")
+    try:
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            step()
+            torch.cuda.synchronize()
+    finally:
+        for cls, (f, b) in saved.items():
+            cls.forward, cls.backward = staticmethod(f), staticmethod(b)
+    # attribute every kernel to "inside an engine autograd node" or "model side" via the CPU op that launched it
+    inside, outside = {}, {}
+    for ev in prof.events():
+        ks = getattr(ev, "kernels", None)
+        if not ks:
+            continue
+        anc, tag = ev, None
+        while anc is not None:
+            if anc.name in ("lyco_node_fwd", "lyco_node_bwd"):
+                tag = anc.name
+                break
+            anc = anc.cpu_parent
+        for k in ks:
+            name = k.name.split("<")[0][:70]
+            dst = inside if tag else outside
+            a = dst.setdefault(name, [0, 0.0])
+            a[0] += 1
+            a[1] += k.duration
+    if args.kernel_table:
+        with open(args.kernel_table + ".attribution", "w") as fh:
+            for title, d in (("launched inside the engine's autograd nodes", inside), ("model side (outside)", outside)):
+                tot_d = sum(v[1] for v in d.values())
+                fh.write(f"{title}: {tot_d / 1e3:.2f} ms\n")
+                for name, (cnt, t) in sorted(d.items(), key=lambda kv: -kv[1][1])[:14]:
+                    fh.write(f"{t / 1e3:10.3f} ms {cnt:6d}  {name}\n")
+    agg = {}
+    for ev in prof.events():
+        if (ev.device_type is not None and str(ev.device_type).endswith("CUDA") and ev.device_time_total > 0
+                and not ev.name.startswith("lyco_node_")):
+            name = ev.name.split("<")[0][:90]
+            a = agg.setdefault(name, [0, 0.0])
+            a[0] += 1
+            a[1] += ev.device_time_total
+    tot = sum(v[1] for v in agg.values())
+    gemm_kernel_ms = sum(v[1] for k, v in agg.items() if "gemm_sm100_kernel" in k) / 1e3
+    kernel_ms = {}
+    for k, v in agg.items():
+        if "lyco::" in k or k.startswith("lyco"):
+            short = k.replace("void ", "").replace("lyco::", "").split("(")[0]
+            kernel_ms[short] = round(kernel_ms.get(short, 0.0) + v[1] / 1e3, 3)
+    kernel_ms["_all_kernels_of_the_step"] = round(tot / 1e3, 2)
+    if args.kernel_table:
+        with open(args.kernel_table, "w") as fh:
+            fh.write(f"one eager step, CUDA kernels by total device time (us); sum = {tot / 1e3:.2f} ms\n")
+            for name, (cnt, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                fh.write(f"{t / 1e3:10.3f} ms {100 * t / tot:5.1f}% {cnt:6d}  {name}\n")
+    return gemm_kernel_ms, kernel_ms
+
+
+# ------------------------------------------------------------------ reference on the GPU (PyTorch eager)
+def gpu_eager_reference(args, unet, engine_net, static, engine_loss):
+    """Time the UNMODIFIED reference (baseline/_ref, ``lycoris.kohya.create_network`` -> ``apply_to``) on the same
+    model, the same adapter parameters (engine state_dict loaded into the reference network — the wire format is
+    shared) and the same inputs, PyTorch-eager under autocast: the denominator of BASELINE.json's >=4x target."""
+    import torch
+    import torch.nn.functional as F
+
+    wl = args.wl
+    ref_kohya, notes = import_reference()
+    if ref_kohya is None:
+        return {"unavailable": notes}
+    device = static["sample"].device
+    sd = {k: v.detach().clone() for k, v in engine_net.state_dict().items()}
+    engine_net.restore()
+    try:
+        net = create_network(ref_kohya, wl, unet)
+        net.apply_to(None, unet, False, True)
+        net.to(device)
+        missing = net.load_state_dict(sd, strict=False)
+        n_missing = len(missing.missing_keys) + len(missing.unexpected_keys)
+        net.requires_grad_(True)
+        net.train()
+
+        def step():
+            for p in net.parameters():
+                p.grad = None
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                out = unet(static["sample"], static["timesteps"], static["context"], static.get("added_cond"))
+            loss = F.mse_loss(out.float(), static["target"].float())
+            loss.backward()
+            return loss
+
+        for _ in range(3):
+            loss = step()
+        torch.cuda.synchronize()
+        ref_loss = float(loss)
+        n = max(1, args.ref_steps)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        rel = abs(engine_loss - ref_loss) / max(abs(ref_loss), 1e-12)
+        out = {
+            "value": 1000.0 / ms, "unit": "steps/s", "ms_per_step": ms, "steps": n, "warmup": 3,
+            "source": "unmodified reference from baseline/_ref (pip install --no-deps --target of /root/reference), "
+                      "lycoris.kohya.create_network + apply_to, PyTorch eager, bf16 autocast, same model / parameters / inputs",
+            "loss": ref_loss, "engine_loss": engine_loss, "loss_rel_diff": rel, "loss_check": "ok" if rel <= 2e-2 else "FAILED",
+            "state_dict_key_mismatches": n_missing,
+        }
+        if notes:
+            out["reference_notes"] = notes
+        for lora in list(getattr(net, "loras", [])):
+            lora.restore()
+        del net
+        assert rel <= 2e-2, f"engine loss {engine_loss} vs reference loss {ref_loss}: relative difference {rel:.3e} > 2e-2"
+        return out
+    finally:
+        torch.cuda.empty_cache()
+
+
+def run_reference_gpu(args):
+    """Standalone arm: only the unmodified reference on one GPU (for profiling it, or when the engine is absent)."""
+    import torch
+
+    import lycoris_b200.kohya as kohya
+    from workloads.unet_skeleton import UNetSkeleton
+
+    if int(os.environ.get("RANK", 0)) != 0:
+        return
+    wl = args.wl
+    torch.cuda.set_device(0)
+    device = torch.device("cuda", 0)
+    cfg = model_cfg(wl["model"])
+    torch.manual_seed(0)
+    unet = UNetSkeleton(cfg).to(device=device, dtype=torch.bfloat16)
+    unet.requires_grad_(False)
+    unet.train()
+    # the engine's network is built only to obtain the (seeded, perturbed) adapter parameters; it never runs
+    net = create_network(kohya, wl, unet)
+    net.apply_to(None, unet, False, True)
+    net.to(device)
+    perturb_zero_factors(net, 1)
+    batch = unet.synthetic_batch(wl["batch"], "cpu", torch.bfloat16, seed=2, sample_size=args.sample_size or None)
+    st = {k: (v.to(torch.bfloat16) if v.is_floating_point() else v).to(device) for k, v in batch.items()}
+    for k in ("sample", "target"):
+        st[k] = st[k].contiguous(memory_format=torch.channels_last)
+    args.ref_steps = args.steps
+    try:
+        ref = gpu_eager_reference(args, unet, net, st, float("nan"))
+    except AssertionError:
+        ref = {}
+    print(json.dumps({"metric": f"{cfg.name.upper()}-UNet+{wl['label']} fwd+bwd steps/sec", "impl": "reference-gpu",
+                      "value": ref.get("value"), "unit": "steps/s", "ms_per_step": ref.get("ms_per_step"), "n_gpus": 1,
+                      "steps": args.steps, "warmup": 3, "dtype": "bf16", "data": "synthetic", "detail": ref,
+                      "config": {"workload": f"{wl['name']}: {cfg.name} + {wl['label']}, batch {wl['batch']}, eager ATen path"}}),
+          flush=True)
+
+
+# ------------------------------------------------------------------ reference on the host cores
+def wrapped_layer_signatures(args):
+    """Distinct (adapter class, base layer geometry, adapter settings, rows) of the workload with multiplicity,
+    enumerated by building the engine's network on a META-device skeleton (no weights) and running a meta
+    forward with hooks on the wrapped layers."""
     import torch
     import torch.nn as nn
 
+    import lycoris_b200.kohya as kohya
     from workloads.unet_skeleton import UNetSkeleton
 
-    cfg = model_cfg(args.model)
+    wl = args.wl
+    cfg = model_cfg(wl["model"])
     with torch.device("meta"):
         unet = UNetSkeleton(cfg)
-    targets = ("Transformer2DModel", "ResnetBlock2D", "Downsample2D", "Upsample2D")
-    layers = {}
-    for _, mod in unet.named_modules():
-        if mod.__class__.__name__ in targets:
-            for _, sub in mod.named_modules():
-                if isinstance(sub, (nn.Linear, nn.Conv2d)):
-                    layers[id(sub)] = sub
-    shapes = {}
+    net = create_network(kohya, wl, unet)
+    info = {}
+    hooks = []
+    for lora in net.loras:
+        org = lora.org_module[0]
 
-    def hook(m, inp, out):
-        x = inp[0]
-        if isinstance(m, nn.Linear):
-            key = ("linear", m.out_features, m.in_features, 1, 1, x.numel() // x.shape[-1] // args.batch, 0)
-        else:
-            key = ("conv", m.out_channels, m.in_channels, m.kernel_size[0], m.stride[0], x.shape[-1], m.padding[0])
-        shapes[key] = shapes.get(key, 0) + 1
+        def hook(m, inp, out, _l=lora):
+            x = inp[0]
+            kind = type(_l).__name__
+            extra = ()
+            if kind == "LokrModule":
+                w1 = _l.lokr_w1 if _l.use_w1 else _l.lokr_w1_a
+                extra = (int(w1.shape[0]), bool(_l.use_w2))
+            elif kind == "IA3Module":
+                extra = (bool(_l.train_input),)
+            if isinstance(m, nn.Linear):
+                geo = ("linear", m.out_features, m.in_features, 1, 1, 0, x.numel() // x.shape[-1])
+            else:
+                geo = ("conv", m.out_channels, m.in_channels, m.kernel_size[0], m.stride[0], m.padding[0], x.shape[-1])
+            key = (kind, geo, int(getattr(_l, "lora_dim", 0) or 0), float(_l.alpha) if hasattr(_l, "alpha") else 0.0, extra)
+            info[key] = info.get(key, 0) + 1
 
-    hs = [m.register_forward_hook(hook) for m in layers.values()]
+        hooks.append(org.register_forward_hook(hook))
     s = args.sample_size or cfg.sample_size
+    b = wl["batch"]
     with torch.no_grad():
-        b = {
-            "sample": torch.zeros(args.batch, cfg.in_channels, s, s, device="meta"),
-            "t": torch.zeros(args.batch, device="meta", dtype=torch.long),
-            "ctx": torch.zeros(args.batch, cfg.context_len, cfg.cross_attention_dim, device="meta"),
-            "add": torch.zeros(args.batch, cfg.addition_embed_dim, device="meta") if cfg.addition_embed_dim else None,
-        }
-        unet(b["sample"], b["t"], b["ctx"], b["add"])
-    for h in hs:
+        unet(torch.zeros(b, cfg.in_channels, s, s, device="meta"), torch.zeros(b, device="meta", dtype=torch.long),
+             torch.zeros(b, cfg.context_len, cfg.cross_attention_dim, device="meta"),
+             torch.zeros(b, cfg.addition_embed_dim, device="meta") if cfg.addition_embed_dim else None)
+    for h in hooks:
         h.remove()
-    return shapes
+    return info
 
 
-def cpu_reference(args, budget_s=20.0):
-    """The reference's CPU path (oracle port of lycoris/modules/lokr.py forward, autograd backward),
-    timed on this box's host cores on a BOUNDED sample: every distinct wrapped-layer shape of the
-    workload is run fwd+bwd at a reduced number of rows / reduced spatial size, scaled linearly to
-    the full M and multiplied by its multiplicity; un-wrapped ops (attention, norms) are not counted,
-    which flatters the CPU.  fp32 (the reference's CPU-runnable regime)."""
+def _reference_module_factory():
+    """Adapter classes of the unmodified reference (baseline/_ref) when vendored — else the oracle port."""
+    ref_kohya, _ = import_reference()
+    if ref_kohya is None:
+        return None
+    import lycoris.modules.ia3 as r_ia3
+    import lycoris.modules.locon as r_locon
+    import lycoris.modules.loha as r_loha
+    import lycoris.modules.lokr as r_lokr
+
+    return {"LoConModule": r_locon.LoConModule, "LohaModule": r_loha.LohaModule, "LokrModule": r_lokr.LokrModule,
+            "IA3Module": r_ia3.IA3Module}
+
+
+def cpu_reference(args, budget_s=20.0, reps=3):
+    """The reference's CPU path — its own adapter classes from baseline/_ref wrapped on fp32 base layers, forward +
+    autograd backward — timed on this box's host cores on a BOUNDED sample of the workload: every distinct wrapped
+    layer (class, geometry, settings) is run at TWO reduced row counts (best of ``reps`` each), a line
+    t = a + b*rows is fitted — ``a`` is the M-independent weight-side work (factor products, kron, W + dW),
+    ``b`` the per-row contraction cost — and extrapolated to the layer's full row count, times its multiplicity.
+    Un-wrapped ops (attention, norms) are not counted, which flatters the CPU.  fp32 (the reference's CPU regime)."""
     import torch
-
-    from oracle import lyco_oracle as O
+    import torch.nn as nn
 
     threads = torch.get_num_threads()
-    shapes = distinct_wrapped_shapes(args)
-    total_full = 0.0
+    classes = _reference_module_factory()
+    kind = "reference" if classes is not None else "port"
+    if classes is None:
+        import lycoris_b200.modules as M  # constructor-compatible; only the shapes are used, the oracle does the math
+        from oracle import lyco_oracle as O
+
+        classes = {"LoConModule": M.LoConModule, "LohaModule": M.LohaModule, "LokrModule": M.LokrModule,
+                   "IA3Module": M.IA3Module}
+    sigs = wrapped_layer_signatures(args)
+    batch = args.wl["batch"]
     t_start = time.time()
-    per_shape_budget = budget_s / max(1, len(shapes))
-    sampled = 0
-    for (kind, N, Kd, ks, stride, m, pad), count in shapes.items():
+    total_full = 0.0
+    weight_side = 0.0
+    deadline = t_start + budget_s
+    n_timed = 0
+    for (cls_name, geo, dim, alpha, extra), count in sorted(sigs.items(), key=lambda kv: -kv[1]):
+        gk, N, Kd, ks, stride, pad, m = geo
         torch.manual_seed(0)
-        (a, b), (c, d) = O.factorization(N, 8), O.factorization(Kd, 8)
-        if kind == "linear":
-            rows_full = m * args.batch
-            rows = max(8, min(rows_full, 256))
-            x = torch.randn(rows, Kd)
-            W = torch.randn(N, Kd) * 0.02
-            p = {"lokr_w1": torch.randn(a, c) * 0.1, "lokr_w2": torch.randn(b, d) * 0.02}
-            conv = None
-            scale_up = rows_full / rows
+        if gk == "linear":
+            base = nn.Linear(Kd, N)
+            rows_full = m
+            rows = sorted({max(8, min(rows_full, 64)), max(8, min(rows_full, 256))})
+            mk = [lambda r=r: torch.randn(r, Kd) for r in rows]
         else:
+            base = nn.Conv2d(Kd, N, ks, stride, pad)
             side_full = m
-            side = max(8, min(side_full, 16))
-            x = torch.randn(1, Kd, side, side)
-            W = torch.randn(N, Kd, ks, ks) * 0.02
-            p = {"lokr_w1": torch.randn(a, c) * 0.1, "lokr_w2": torch.randn(b, d, ks, ks) * 0.02}
-            conv = dict(stride=(stride, stride), padding=(pad, pad), dilation=(1, 1), groups=1)
-            scale_up = args.batch * (side_full / side) ** 2
-        bias = torch.zeros(N)
-        cfg = {"scale": 1.0, "multiplier": 1.0}
-        # time: at least one rep, stop at this shape's share of the budget
-        reps, t_acc = 0, 0.0
-        while reps < 1 or (t_acc < per_shape_budget * 0.5 and reps < 3):
-            t0 = time.perf_counter()
-            xx = x.clone().requires_grad_(True)
-            leaves = {k: v.clone().requires_grad_(True) for k, v in p.items()}
-            out = O.layer_forward("lokr", xx, W, bias, leaves, cfg, conv)
-            out.float().pow(2).mean().backward()
-            t_acc += time.perf_counter() - t0
-            reps += 1
-        total_full += (t_acc / reps) * scale_up * count
-        sampled += 1
+            rows_full = batch * ((side_full + 2 * pad - ks) // stride + 1) ** 2
+            sides = sorted({max(4, min(side_full, 8)), max(4, min(side_full, 16))})
+            rows = [((sd_ + 2 * pad - ks) // stride + 1) ** 2 for sd_ in sides]
+            mk = [lambda sd_=sd_: torch.randn(1, Kd, sd_, sd_) for sd_ in sides]
+        base.requires_grad_(False)
+        kw = {}
+        if cls_name == "LokrModule":
+            kw["factor"] = extra[0]
+        if cls_name == "IA3Module":
+            kw["train_on_input"] = extra[0]
+        mod = classes[cls_name]("bench", base, 1.0, dim or 4, alpha or 1, 0.0, 0.0, 0.0, False, **kw)
+        with torch.no_grad():
+            for p in mod.parameters():
+                if float(p.abs().sum()) == 0.0:
+                    p.normal_(0, 0.01)
+        mod.apply_to()
+        ts = []
+        over = time.time() > deadline
+        for make in mk:
+            best = None
+            for _ in range(1 if over else reps):
+                x = make().requires_grad_(True)
+                for p in mod.parameters():
+                    p.grad = None
+                t0 = time.perf_counter()
+                if kind == "reference":
+                    y = base(x)
+                else:
+                    y = _oracle_forward(O, mod, base, x)
+                y.float().pow(2).mean().backward()
+                dt = time.perf_counter() - t0
+                best = dt if best is None else min(best, dt)
+            ts.append(best)
+        if hasattr(mod, "restore"):
+            mod.restore()
+        if len(rows) == 2 and rows[1] > rows[0]:
+            b_ = max(0.0, (ts[1] - ts[0]) / (rows[1] - rows[0]))
+            a_ = max(0.0, ts[0] - b_ * rows[0])
+        else:
+            a_, b_ = 0.0, ts[0] / rows[0]
+        total_full += (a_ + b_ * rows_full) * count
+        weight_side += a_ * count
+        n_timed += 1
     steps_per_s = 1.0 / total_full if total_full > 0 else 0.0
     return {
-        "value": steps_per_s, "unit": "steps/s", "cores": threads, "kind": "port",
-        "sample": f"oracle (torch-CPU restatement of the reference path), fp32, {sampled} distinct wrapped-layer shapes "
-                  f"timed fwd+bwd at <=256 rows / <=16x16 spatial, scaled linearly to batch {args.batch} and multiplied "
-                  f"by multiplicity; un-wrapped ops excluded; extrapolated; {time.time() - t_start:.1f}s of CPU work",
+        "value": steps_per_s, "unit": "steps/s", "cores": threads, "kind": kind,
+        "sample": f"{'unmodified reference modules (baseline/_ref)' if kind == 'reference' else 'oracle port'} on fp32 "
+                  f"CPU base layers; {n_timed} distinct wrapped layers (class, geometry, settings) timed fwd+bwd at two "
+                  f"row counts (<=64 / <=256 rows, <=8x8 / <=16x16 spatial), best of {reps}, line fit t = a + b*rows "
+                  f"extrapolated to the full rows and multiplied by multiplicity; un-wrapped ops excluded; "
+                  f"{time.time() - t_start:.1f}s of CPU work",
         "extrapolated_s_per_step": total_full,
+        "weight_side_s_per_step": weight_side,
         "host_cpus": os.cpu_count(),
     }
 
 
+def _oracle_forward(O, mod, base, x):
+    conv = None
+    if mod.module_type.startswith("conv"):
+        conv = dict(stride=base.stride, padding=base.padding, dilation=base.dilation, groups=base.groups)
+    algo = {"LoConModule": "locon", "LohaModule": "loha", "LokrModule": "lokr", "IA3Module": "ia3"}[type(mod).__name__]
+    cfg = {"scale": getattr(mod, "scale", 1.0), "multiplier": 1.0}
+    if algo == "ia3":
+        cfg["train_on_input"] = mod.train_input
+    return O.layer_forward(algo, x, base.weight, base.bias, dict(mod.named_parameters()), cfg, conv)
+
+
 def run_reference_cpu(args):
+    """--impl reference: each step is ONE bounded sample of the workload through the reference's CPU path (see
+    cpu_reference); the line reports the median over the K timed samples."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    cfg = model_cfg(args.model)
-    vals = []
-    for _ in range(max(1, min(args.warmup, 1))):
-        cpu_reference(args, budget_s=min(5.0, args.cpu_seconds))
-    for _ in range(max(1, args.steps if args.steps < 3 else 3)):
-        vals.append(cpu_reference(args, budget_s=args.cpu_seconds))
-    best = max(vals, key=lambda r: r["value"])
+    wl = args.wl
+    cfg = model_cfg(wl["model"])
+    per_step = max(2.0, min(args.cpu_seconds, 150.0 / max(1, args.steps + min(args.warmup, 1))))
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference(args, budget_s=per_step, reps=1)
+    vals = [cpu_reference(args, budget_s=per_step, reps=2) for _ in range(max(1, args.steps))]
+    vals.sort(key=lambda r: r["value"])
+    med = vals[len(vals) // 2]
+    spread = (vals[-1]["value"] - vals[0]["value"]) / med["value"] if med["value"] else None
     result = {
-        "metric": "SDXL-UNet+LoKr fwd+bwd steps/sec", "value": best["value"], "unit": "steps/s",
+        "metric": f"{cfg.name.upper()}-UNet+{wl['label']} fwd+bwd steps/sec", "value": med["value"], "unit": "steps/s",
         "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1000.0 * best["extrapolated_s_per_step"], "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": 1000.0 * med["extrapolated_s_per_step"], "higher_is_better": True,
+        "scaling": "strong" if wl.get("global_batch") else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-        # the engine arm's workload, timed on the host cores through the oracle port of the reference path
-        "config": {"workload": f"{cfg.name}-unet-skeleton + {args.algo} ({ALGO_NOTE[args.algo]}), preset full, "
-                               f"per-GPU batch {args.batch}, latents {args.sample_size or cfg.sample_size}^2, fwd+bwd, "
-                               "reference path (oracle port) on the host CPU, fp32",
-                   "global_batch": args.batch, "parallelism": "cpu", "sample": best["sample"]},
-        "cpu_baseline": best,
-        "e2e": {"value": best["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": f"{wl['name']}: {cfg.name}-unet-skeleton + {wl['label']} ({wl['note']}), per-GPU batch "
+                               f"{wl['batch']}, latents {args.sample_size or cfg.sample_size}^2, fwd+bwd, the reference's "
+                               f"CPU path ({med['kind']}) on the host cores, fp32",
+                   "global_batch": wl["batch"], "parallelism": "cpu", "sample": med["sample"],
+                   "spread_over_steps": spread},
+        "cpu_baseline": med,
+        "e2e": {"value": med["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(result), flush=True)
-
-
-def run_reference_gpu(args):
-    """Informational: what the reference's eager path costs on this GPU.  Uses the unmodified
-    reference if it was pip-installed into baseline/_ref, else the oracle's per-layer forward
-    (same ATen calls) patched onto every wrapped layer."""
-    import torch
-    import torch.nn.functional as F
-
-    torch.cuda.set_device(0)
-    device = torch.device("cuda", 0)
-    from workloads.unet_skeleton import UNetSkeleton
-
-    cfg = model_cfg(args.model)
-    torch.manual_seed(0)
-    unet = UNetSkeleton(cfg).to(device=device, dtype=torch.bfloat16).to(memory_format=torch.channels_last)
-    unet.requires_grad_(False)
-    unet.train()
-    na = network_args(args.algo)
-    ref_dir = os.path.join(ROOT, "baseline", "_ref")
-    source = "oracle-patched layers"
-    if os.path.isdir(os.path.join(ref_dir, "lycoris")):
-        sys.path.insert(0, ref_dir)
-        import lycoris.kohya as ref_kohya
-
-        torch.manual_seed(1)
-        net = ref_kohya.create_network(1.0, na["network_dim"], na["network_alpha"], None, None, unet, **na["kw"])
-        net.apply_to(None, unet, False, True)
-        net.to(device)
-        source = "unmodified reference from baseline/_ref"
-    else:
-        import lycoris_b200.kohya as kohya
-        from oracle import lyco_oracle as O
-
-        torch.manual_seed(1)
-        net = kohya.create_network(1.0, na["network_dim"], na["network_alpha"], None, None, unet, **na["kw"])
-        for lora in net.loras:
-            net.add_module(lora.lora_name, lora)
-        net.to(device)
-        for lora in net.loras:  # patch the oracle's forward instead of the engine's
-            org = lora.org_module[0]
-            conv = None
-            if lora.module_type.startswith("conv"):
-                conv = dict(stride=org.stride, padding=org.padding, dilation=org.dilation, groups=org.groups)
-
-            def fwd(x, _l=lora, _o=org, _c=conv):
-                p = {k: v for k, v in _l.named_parameters()}
-                return O.layer_forward("lokr", x, _o.weight, _o.bias, p, {"scale": _l.scale, "multiplier": 1.0}, _c)
-
-            org.forward = fwd
-    perturb_zero_factors(net, 1)
-    net.requires_grad_(True)
-    batch = unet.synthetic_batch(args.batch, "cpu", torch.bfloat16, seed=2, sample_size=args.sample_size or None)
-    st = {k: (v.to(torch.bfloat16) if v.is_floating_point() else v).to(device) for k, v in batch.items()}
-    for k in ("sample", "target"):
-        st[k] = st[k].contiguous(memory_format=torch.channels_last)
-
-    def step():
-        for p in net.parameters():
-            p.grad = None
-        with torch.autocast("cuda", dtype=torch.bfloat16):
-            out = unet(st["sample"], st["timesteps"], st["context"], st.get("added_cond"))
-        F.mse_loss(out.float(), st["target"].float()).backward()
-
-    for _ in range(max(3, args.warmup)):
-        step()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / args.steps
-    print(json.dumps({"metric": "SDXL-UNet+LoKr fwd+bwd steps/sec", "impl": "reference-gpu", "source": source,
-                      "value": 1000.0 / ms, "unit": "steps/s", "ms_per_step": ms, "n_gpus": 1, "steps": args.steps,
-                      "warmup": args.warmup, "dtype": "bf16", "data": "synthetic",
-                      "config": {"workload": f"{cfg.name} + {args.algo}, batch {args.batch}, eager ATen path"}}), flush=True)
 
 
 def main():

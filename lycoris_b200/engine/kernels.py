@@ -105,6 +105,8 @@ def conv2d_supported(x, weight_shape, stride, padding, dilation, groups, dtype=N
     (Activations must be NHWC; callers convert NCHW tensors with one transpose pass.)"""
     if x.dim() != 4 or len(weight_shape) != 4 or (dtype or x.dtype) not in (torch.bfloat16, torch.float16):
         return False
+    if x.numel() == 0:
+        return False  # empty batch: nothing to launch, the library handles the bookkeeping
     O, C, R, S = weight_shape
     if groups != 1 or tuple(dilation) != (1, 1) or stride[0] != stride[1] or not (1 <= stride[0] <= 8):
         return False

@@ -75,24 +75,26 @@ def _uniform_factors(factors):
 
 # --------------------------------------------------------------------------- dense
 def _dense_nt(a, b, bias=None):
-    """a[M,K] · b[N,K]ᵀ (+ bias) — forward contraction."""
-    if K.gemm_supported(a, b):
+    """a[M,K] · b[N,K]ᵀ (+ bias) — forward contraction.  The output [M, N] has row pitch N, so N must be
+    TMA-addressable too (lyco_gemm rejects ldc % 8 != 0); an empty batch has nothing to launch."""
+    if a.shape[0] > 0 and b.shape[0] % 8 == 0 and K.gemm_supported(a, b):
         return K.gemm(a, b, bias=bias)
-    warning_once("lycoris_b200: a layer shape is not TMA-addressable (needs multiples of 8); "
-                 "that layer's contraction uses the library GEMM")
+    if a.shape[0] > 0:
+        warning_once("lycoris_b200: a layer shape is not TMA-addressable (needs multiples of 8); "
+                     "that layer's contraction uses the library GEMM")
     return F.linear(a, b, bias)
 
 
 def _dense_nn(a, b):
     """a[M,N] · b[N,K] — dgrad contraction (b consumed MN-major, no transpose copy)."""
-    if K.gemm_supported(a, b):
+    if a.shape[0] > 0 and b.shape[1] % 8 == 0 and K.gemm_supported(a, b):
         return K.gemm(a, b, b_mn=True)
     return a @ b
 
 
 def _dense_tn_f32(a, b):
     """a[M,N]ᵀ · b[M,K] -> fp32 [N,K] — wgrad contraction, reduction split across CTAs."""
-    if K.gemm_supported(a, b):
+    if a.shape[0] > 0 and b.shape[1] % 8 == 0 and K.gemm_supported(a, b):
         return K.gemm(a, b, a_mn=True, b_mn=True, out_dtype=torch.float32)
     return (a.t() @ b).float()
 
@@ -119,7 +121,10 @@ def _dense3(a, b, *, a_mn=False, b_mn=False, init=None):
 
 
 def _f32_supported(*mats):
-    return all(t.dim() == 2 and t.is_contiguous() and t.shape[1] % 8 == 0 and t.dtype == torch.float32 for t in mats)
+    """fp32 Linear on the engine: both dims of W are a row pitch of some operand or output
+    (W[N,K]: K for X / W, N for Y / dY), so both must be multiples of 8."""
+    return all(t.dim() == 2 and t.is_contiguous() and t.shape[0] % 8 == 0 and t.shape[1] % 8 == 0
+               and t.dtype == torch.float32 for t in mats)
 
 
 class _MergedContractionF32(torch.autograd.Function):
@@ -389,6 +394,12 @@ def _conv_params(module):
     }
 
 
+def _base_trainable(org):
+    """The base layer itself is being fine-tuned (joint training, a trainable bias): its gradient has to come
+    from ``org_forward`` like in the reference, so the engine must not swallow the base contraction."""
+    return org.weight.requires_grad or (org.bias is not None and org.bias.requires_grad)
+
+
 def adapter_forward(module, x, args, kwargs, native_spec, assemble_fallback):
     """Rebuild-mode forward of one adapter on the engine (called from ``Module.forward``)."""
     if not x.is_cuda:
@@ -397,6 +408,10 @@ def adapter_forward(module, x, args, kwargs, native_spec, assemble_fallback):
             f"got a {x.device.type} input for {module.lora_name!r}. There is no CPU fallback — "
             "use the reference implementation for CPU runs."
         )
+    if x.device.index != torch.cuda.current_device():
+        # the C-ABI launches on the CURRENT device and stream: enter the tensor's device first
+        with torch.cuda.device(x.device):
+            return adapter_forward(module, x, args, kwargs, native_spec, assemble_fallback)
     org = module.org_module[0]
     W = org.weight.detach()
     bias = None if org.bias is None else org.bias.detach()
@@ -430,7 +445,7 @@ def adapter_forward(module, x, args, kwargs, native_spec, assemble_fallback):
         y = adapter_forward_pointwise(module, x, W, bias, ac, native_spec, assemble_fallback, args, kwargs)
         return y
 
-    plain = module._is_outermost_on_plain_forward() and not args and not kwargs
+    plain = module._is_outermost_on_plain_forward() and not args and not kwargs and not _base_trainable(org)
     base = None
     if not plain:
         # another wrapper sits below us (stacking) or the base forward takes extra arguments:
@@ -454,7 +469,8 @@ def _adapter_forward_f32(module, x, args, kwargs, W, bias, assemble_fallback):
     bf16 products on the engine; convolutions and unaligned shapes use the library."""
     if x.dtype != torch.float32:
         raise RuntimeError(f"lycoris_b200: input dtype {x.dtype} != weight dtype torch.float32 (no autocast active)")
-    plain = module._is_outermost_on_plain_forward() and not args and not kwargs
+    plain = (module._is_outermost_on_plain_forward() and not args and not kwargs
+             and not _base_trainable(module.org_module[0]))
     base = None if plain else module.org_forward(x, *args, **kwargs)
     Wm = assemble_fallback(W)
     if not plain:
@@ -471,7 +487,8 @@ def _adapter_forward_f32(module, x, args, kwargs, W, bias, assemble_fallback):
 def adapter_forward_pointwise(module, x, W, bias, ac, native_spec, assemble_fallback, args, kwargs):
     """channels_last 1x1 conv: [B,C,H,W] (NHWC storage) -> [B*H*W, C] linear -> NHWC output."""
     B, C, H, Wd = x.shape
-    plain = module._is_outermost_on_plain_forward() and not args and not kwargs
+    plain = (module._is_outermost_on_plain_forward() and not args and not kwargs
+             and not _base_trainable(module.org_module[0]))
     base = None if plain else module.org_forward(x, *args, **kwargs)
     x2 = x.permute(0, 2, 3, 1).reshape(B * H * Wd, C)
     W2 = W.reshape(W.shape[0], C)

@@ -245,13 +245,14 @@ class LycorisBaseModule(ModuleCustomSD):
             module.__dict__.pop("_lycoris_original_forward", None)
 
     def _is_outermost_on_plain_forward(self):
-        """True when ``org_forward`` is the base layer's own forward (no wrapper below us)."""
+        """True only when ``org_forward`` is the base layer's OWN class forward bound to that layer — no
+        LyCORIS wrapper below us and no foreign instance patch (kohya ``networks.lora``, an accelerate
+        offload hook, a custom forward).  Only then may the engine contract ``x . (W + dW)^T + b`` directly
+        from ``org.weight``; anything else keeps ``org_forward(x)`` and adds the delta contraction, like
+        the reference (base.py:264-287)."""
         module = self.org_module[0]
-        pristine = getattr(module, "_lycoris_original_forward", None)
         below = self.org_forward
-        if pristine is not None:
-            return below is pristine or getattr(below, "__func__", None) is getattr(pristine, "__func__", object())
-        return getattr(below, "__self__", None) is module
+        return getattr(below, "__self__", None) is module and getattr(below, "__func__", None) is type(module).forward
 
     # ----------------------------------------------------------------------- merge
     def _retarget(self):
@@ -399,11 +400,26 @@ class LycorisBaseModule(ModuleCustomSD):
             self._scalar_cache = v
         return v
 
+    def _forbid_capture(self, what):
+        """Host-side random draws (the reference's ``torch.rand(1)`` module-dropout coin, its CPU rank-dropout
+        masks, DyLoRA's ``random.randint``) are evaluated ONCE when a step is captured into a CUDA graph and
+        every replay would train the same frozen choice: refuse instead of silently freezing."""
+        if torch.cuda.is_available() and torch.cuda.is_current_stream_capturing():
+            raise RuntimeError(
+                f"lycoris_b200: {what} of {self.lora_name!r} draws from the HOST random stream on every step "
+                "(as the reference does) and would be frozen into the captured CUDA graph; run this step "
+                "eagerly, or set the dropout to 0 / use a fixed-rank algorithm for graph-captured training")
+
     def _module_dropped(self):
-        return bool(self.module_dropout and self.training and torch.rand(1) < self.module_dropout)
+        if not (self.module_dropout and self.training):
+            return False
+        self._forbid_capture("module_dropout")
+        return bool(torch.rand(1) < self.module_dropout)
 
     def _rank_drop_rows(self, weight, device=None):
         """Bernoulli mask over output rows of dW (rebuild-mode rank dropout)."""
+        if device is None or torch.device(device).type != "cuda":
+            self._forbid_capture("rank_dropout (mask drawn on the CPU)")
         drop = (torch.rand(weight.size(0), device=device) > self.rank_dropout).to(weight.dtype)
         drop = drop.view(-1, *[1] * (weight.dim() - 1)).to(weight.device)
         if self.rank_dropout_scale:

@@ -92,6 +92,7 @@ class DyLoraModule(LycorisBaseModule):
         return down, up, self.alpha / (b + 1)
 
     def get_random_rank_weight(self):
+        self._forbid_capture("DyLoRA's per-step rank sample (random.randint)")
         b = random.randint(0, self.block_count - 1)
         return self.get_weight(b * self.block_size)
 
@@ -119,6 +120,7 @@ class DyLoraModule(LycorisBaseModule):
         from ..engine.kernels import ALGO_DYLORA
         from ..engine.ops import NativeSpec
 
+        self._forbid_capture("DyLoRA's per-step rank sample (random.randint)")
         b = random.randint(0, self.block_count - 1)  # same host RNG draw as get_random_rank_weight
         down, up, b = self._blocks(b * self.block_size)
         return NativeSpec(

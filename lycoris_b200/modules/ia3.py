@@ -122,10 +122,6 @@ class IA3Module(LycorisBaseModule):
     def _assemble(self, base_weight):
         return self.get_merged_weight(multiplier=self.multiplier)[0].to(base_weight.device, dtype=base_weight.dtype)
 
-    def _is_outermost_on_plain_forward(self):
-        # IA3.apply_to does not maintain the wrapper stack: compare against the base layer directly
-        return getattr(self.org_forward, "__self__", None) is self.org_module[0]
-
     def forward(self, x, *args, **kwargs):
         if self._module_dropped():
             return self.org_forward(x, *args, **kwargs)
