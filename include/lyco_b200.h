@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define LYCO_ABI_VERSION 2
+#define LYCO_ABI_VERSION 3
 
 /* element types */
 enum { LYCO_BF16 = 0, LYCO_F16 = 1, LYCO_F32 = 2 };
@@ -222,6 +222,73 @@ int lyco_factor_grads(const lyco_delta_desc_t* d, const float* dW, const void* W
  * Hadamard factor, recomputed — lycoris/functional/loha.py:18-30).
  */
 int lyco_grad_prep(const float* dW, const void* P, void* G, int64_t n, float gscale, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* structured LoKr factor gradients (no dense dW')                            */
+/* ------------------------------------------------------------------------- */
+
+/*
+ * out[m, a, c] = sum_b Wm(a, b) * in[m, b, c]   for m < M;  in is [M, nb, nc], out is [M, na, nc] (16-bit, `dtype`),
+ * Wm(a, b) = w[a*ldw + b] (transpose = 0) or w[b*ldw + a] (transpose = 1), w in w_dtype (bf16 / f16 / f32).
+ * nc % 8 == 0, na, nb <= 8, 16-byte aligned arrays.
+ *
+ * With w = lokr_w1 [up, uq] this forms Xt[m,pu,v] = sum_u w1[pu,u] X[m,u,v] from X [M, uq*vq] (transpose = 0) or
+ * Z[m,u,pv] = sum_pu w1[pu,u] dY[m,pu,pv] from dY [M, up*vp] (transpose = 1): the channel-group mix of the
+ * reference's structured Kronecker contraction, lycoris/modules/lokr.py:517-530 (F.linear over the group axis).
+ * Then  g_w2 = lyco_gemm(dY as [M*up, vp]ᵀ, Xt as [M*up, vq])  — one contraction with 1/uq of the FLOPs of the
+ * dense dW' = dYᵀ·X that autograd runs for `delta_weight` (lokr.py:565) — and g_w1 comes from lyco_lokr_w1grad.
+ */
+int lyco_lokr_mix(const void* in, void* out, const void* w, int w_dtype, int ldw, int transpose,
+                  int64_t M, int na, int nb, int nc, int dtype, void* stream);
+
+/*
+ * g_w1[a, b] = gscale * sum_{m, c} P[m, a, c] * R[m, b, c];  P is [M, na, nc], R is [M, nb, nc] (16-bit, `dtype`),
+ * g_w1 fp32 [na, nb], zero-filled by the call.  nc % 8 == 0, na, nb <= 8.
+ * With Q = dY2·w2 ([M*up, vq], one lyco_gemm) and X [M, uq, vq]:  g_w1[pu,u] = sum_{m,v} Q[m,pu,v] X[m,u,v]
+ * (or P = dY, R = H = X2·w2ᵀ when dY is the mixed side).  Replaces torch.kron's backward reduction over the dense
+ * d(delta_weight) for lokr_w1 (lycoris/functional/lokr.py:11-20 under autograd).
+ */
+int lyco_lokr_w1grad(const void* P, const void* R, float* g_w1, int64_t M, int na, int nb, int nc,
+                     float gscale, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* delta weight / DoRA (merge_to, onfly_merge, apply_max_norm, dora_wd)       */
+/* ------------------------------------------------------------------------- */
+
+/*
+ * dW[N,K'] = the adapter's delta weight (the rounding chain above with W left out), written in out_dtype
+ * (LYCO_BF16 / LYCO_F16 / LYCO_F32; dW_out may be NULL when only the norm is wanted), and, when norm_sq != NULL,
+ * *norm_sq += sum dW^2 (fp32; the caller zero-fills it).  Here d->w_dtype may be LYCO_F32: no 16-bit rounding
+ * points, i.e. the arithmetic of the reference's get_diff_weight on fp32 parameters.  `W` is read by IA3 only
+ * (dW = W * w * mult), in d->w_dtype.
+ * Replaces get_diff_weight / make_weight(...).norm() on the merge and max-norm paths:
+ *   lycoris/modules/base.py:326-374 (merge_to / onfly_merge), locon.py:221-237,262-271, loha.py:228-260,
+ *   lokr.py:383-397,442-466, ia3.py:91-111, kohya.py:589-613 (apply_max_norm_regularization).
+ */
+int lyco_delta_weight(const lyco_delta_desc_t* d, const void* W, void* dW_out, int out_dtype, float* norm_sq,
+                      void* stream);
+
+/*
+ * DoRA (dora_wd) around the merged weight Wm = W + dW (16-bit [N,K'], from lyco_merge_weight):
+ *   sumsq[g] = sum over group g of Wm^2      groups: output rows (on_out = 1) or input channels (K'/taps of them)
+ *   s[g]     = dora_scale[g] / (sqrt(sumsq[g]) + eps);   s <- mult*(s - 1) + 1 when mult != 1
+ *   W_out    = rnd_w(Wm * s[group])
+ * sumsq (fp32 [groups]) is zero-filled and written by the call and kept by the caller for the backward.
+ * Replaces apply_weight_decompose, lycoris/modules/locon.py:239-260 (copies in loha.py / lokr.py).
+ */
+int lyco_dora_fwd(const void* Wm, void* W_out, const float* dora_scale, float* sumsq, int N, int K, int on_out,
+                  int taps, float mult, float eps, int w_dtype, void* stream);
+
+/*
+ * Backward of lyco_dora_fwd, in place: dW (fp32 [N,K'], = dYᵀ·X of the contraction with W_out) becomes dWm, and
+ * g_scale[g] (fp32 [groups]) receives the gradient of dora_scale:
+ *   t[g] = sum_g dW*Wm;  n = sqrt(sumsq), ne = n + eps
+ *   g_scale[g] = t * mult / ne;     dWm = s * dW - (mult * dora_scale * t / (ne^2 * n)) * Wm
+ * `t` is fp32 scratch [groups] (zero-filled by the call).  Replaces autograd through apply_weight_decompose.
+ */
+int lyco_dora_bwd(float* dW, const void* Wm, const float* dora_scale, const float* sumsq, float* t,
+                  float* g_scale, int N, int K, int on_out, int taps, float mult, float eps, int w_dtype,
+                  void* stream);
 
 #ifdef __cplusplus
 }

@@ -14,6 +14,8 @@
 #include "gemm_sm100.cuh"
 #include "weight_kernels.cuh"
 #include "layout_kernels.cuh"
+#include "lokr_struct_kernels.cuh"
+#include "dora_kernels.cuh"
 
 namespace {
 
@@ -328,10 +330,10 @@ int pick_splits(long tiles, int k_blocks, int sms) {
   return best;
 }
 
-int check_desc(const lyco_delta_desc_t* d) {
+int check_desc(const lyco_delta_desc_t* d, bool allow_f32_weight = false) {
   if (!d) return fail("null delta descriptor");
   if (d->out_dim <= 0 || d->in_dim <= 0) return fail("bad weight shape %d x %d", d->out_dim, d->in_dim);
-  if (d->w_dtype != LYCO_BF16 && d->w_dtype != LYCO_F16)
+  if (d->w_dtype != LYCO_BF16 && d->w_dtype != LYCO_F16 && !(allow_f32_weight && d->w_dtype == LYCO_F32))
     return fail("weight dtype must be bf16 or f16 (got %d)", d->w_dtype);
   switch (d->algo) {
     case LYCO_ALGO_LOCON:
@@ -798,6 +800,139 @@ int lyco_grad_prep(const float* dW, const void* P, void* G, int64_t n, float gsc
                                                    gscale, dtype);
   LYCO_CUDA(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+int lyco_lokr_mix(const void* in, void* out, const void* w, int w_dtype, int ldw, int transpose, int64_t M, int na,
+                  int nb, int nc, int dtype, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!in || !out || !w) return fail("lyco_lokr_mix: null operand");
+  if (dtype != LYCO_BF16 && dtype != LYCO_F16) return fail("lyco_lokr_mix: activations must be bf16/f16");
+  if (M <= 0 || na < 1 || nb < 1 || na > 8 || nb > 8 || nc < 8 || nc % 8)
+    return fail("lyco_lokr_mix: needs M > 0, 1 <= na, nb <= 8, nc %% 8 == 0 (M=%lld na=%d nb=%d nc=%d)", (long long)M, na, nb, nc);
+  if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15)
+    return fail("lyco_lokr_mix: arrays must be 16-byte aligned");
+  DeviceInfo di;
+  if (device_info(&di)) return 1;
+  const int nc8 = nc / 8;
+  const int64_t work = M * nc8;
+  int64_t grid = (work + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(di.sms) * 16;
+  if (grid > cap) grid = cap;
+  const int fmt = dtype == LYCO_BF16 ? 1 : 0;
+  const uint16_t* src = static_cast<const uint16_t*>(in);
+  uint16_t* dst = static_cast<uint16_t*>(out);
+  if (na <= 4)
+    lyco::lokr_mix_kernel<4><<<static_cast<int>(grid), 256, 0, stream>>>(src, dst, w, w_dtype, ldw, transpose, M, na, nb, nc8, fmt);
+  else
+    lyco::lokr_mix_kernel<8><<<static_cast<int>(grid), 256, 0, stream>>>(src, dst, w, w_dtype, ldw, transpose, M, na, nb, nc8, fmt);
+  LYCO_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+int lyco_lokr_w1grad(const void* P, const void* R, float* g_w1, int64_t M, int na, int nb, int nc, float gscale,
+                     int dtype, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!P || !R || !g_w1) return fail("lyco_lokr_w1grad: null operand");
+  if (dtype != LYCO_BF16 && dtype != LYCO_F16) return fail("lyco_lokr_w1grad: activations must be bf16/f16");
+  if (M <= 0 || na < 1 || nb < 1 || na > 8 || nb > 8 || nc < 8 || nc % 8)
+    return fail("lyco_lokr_w1grad: needs M > 0, 1 <= na, nb <= 8, nc %% 8 == 0 (M=%lld na=%d nb=%d nc=%d)", (long long)M, na, nb, nc);
+  if ((reinterpret_cast<uintptr_t>(P) | reinterpret_cast<uintptr_t>(R)) & 15)
+    return fail("lyco_lokr_w1grad: arrays must be 16-byte aligned");
+  DeviceInfo di;
+  if (device_info(&di)) return 1;
+  LYCO_CUDA(cudaMemsetAsync(g_w1, 0, sizeof(float) * static_cast<size_t>(na) * nb, stream));
+  const int nc8 = nc / 8;
+  const int64_t work = M * nc8;
+  int64_t grid = (work + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(di.sms) * 4;  // few, long-lived CTAs: the final reduction is per CTA
+  if (grid > cap) grid = cap;
+  const int fmt = dtype == LYCO_BF16 ? 1 : 0;
+  const uint16_t* p = static_cast<const uint16_t*>(P);
+  const uint16_t* r = static_cast<const uint16_t*>(R);
+  if (na <= 4 && nb <= 4)
+    lyco::lokr_w1grad_kernel<4, 4><<<static_cast<int>(grid), 256, 0, stream>>>(p, r, g_w1, M, na, nb, nc8, gscale, fmt);
+  else
+    lyco::lokr_w1grad_kernel<8, 8><<<static_cast<int>(grid), 256, 0, stream>>>(p, r, g_w1, M, na, nb, nc8, gscale, fmt);
+  LYCO_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+int lyco_delta_weight(const lyco_delta_desc_t* d, const void* W, void* dW_out, int out_dtype, float* norm_sq,
+                      void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (check_desc(d, /*allow_f32_weight=*/true)) return 1;
+  if (d->algo == LYCO_ALGO_RAW) return fail("lyco_delta_weight: LYCO_ALGO_RAW is a merge-only descriptor");
+  if (d->algo == LYCO_ALGO_IA3 && !W) return fail("lyco_delta_weight: ia3 needs W");
+  if (!dW_out && !norm_sq) return fail("lyco_delta_weight: nothing to compute (no output, no norm)");
+  if (out_dtype != LYCO_BF16 && out_dtype != LYCO_F16 && out_dtype != LYCO_F32)
+    return fail("lyco_delta_weight: bad out_dtype %d", out_dtype);
+  DeviceInfo di;
+  if (device_info(&di)) return 1;
+  const int64_t total = static_cast<int64_t>(d->out_dim) * d->in_dim;
+  int64_t grid = (total + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(di.sms) * 16;
+  if (grid > cap) grid = cap;
+  lyco::delta_weight_kernel<<<static_cast<int>(grid), 256, 0, stream>>>(*d, W, dW_out, out_dtype, norm_sq);
+  LYCO_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+static int dora_check(const char* who, const void* Wm, int N, int K, int on_out, int taps, int w_dtype) {
+  if (!Wm) return fail("%s: null weight", who);
+  if (N <= 0 || K <= 0 || taps <= 0 || (!on_out && K % taps)) return fail("%s: bad shape N=%d K=%d taps=%d", who, N, K, taps);
+  if (w_dtype != LYCO_BF16 && w_dtype != LYCO_F16) return fail("%s: weights must be bf16/f16", who);
+  if ((N + 63) / 64 > 65535) return fail("%s: too many rows", who);
+  return 0;
+}
+
+int lyco_dora_fwd(const void* Wm, void* W_out, const float* dora_scale, float* sumsq, int N, int K, int on_out,
+                  int taps, float mult, float eps, int w_dtype, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (dora_check("lyco_dora_fwd", Wm, N, K, on_out, taps, w_dtype)) return 1;
+  if (!W_out || !dora_scale || !sumsq) return fail("lyco_dora_fwd: null operand");
+  DeviceInfo di;
+  if (device_info(&di)) return 1;
+  const int groups = on_out ? N : K / taps;
+  LYCO_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(float) * groups, stream));
+  const dim3 rgrid(cdiv(K, 256), cdiv(N, 64));
+  const uint16_t* wm = static_cast<const uint16_t*>(Wm);
+  lyco::dora_reduce_kernel<0><<<rgrid, 256, 0, stream>>>(nullptr, wm, sumsq, N, K, on_out, taps, w_dtype);
+  const int64_t total = static_cast<int64_t>(N) * K;
+  int64_t grid = (total + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(di.sms) * 16;
+  if (grid > cap) grid = cap;
+  lyco::dora_apply_fwd_kernel<<<static_cast<int>(grid), 256, 0, stream>>>(wm, static_cast<uint16_t*>(W_out), sumsq, dora_scale,
+                                                                         N, K, on_out, taps, mult, eps, w_dtype);
+  LYCO_CUDA(cudaGetLastError());
+  g_launches.fetch_add(2, std::memory_order_relaxed);
+  return 0;
+}
+
+int lyco_dora_bwd(float* dW, const void* Wm, const float* dora_scale, const float* sumsq, float* t, float* g_scale,
+                  int N, int K, int on_out, int taps, float mult, float eps, int w_dtype, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (dora_check("lyco_dora_bwd", Wm, N, K, on_out, taps, w_dtype)) return 1;
+  if (!dW || !dora_scale || !sumsq || !t) return fail("lyco_dora_bwd: null operand");
+  DeviceInfo di;
+  if (device_info(&di)) return 1;
+  const int groups = on_out ? N : K / taps;
+  LYCO_CUDA(cudaMemsetAsync(t, 0, sizeof(float) * groups, stream));
+  const dim3 rgrid(cdiv(K, 256), cdiv(N, 64));
+  const uint16_t* wm = static_cast<const uint16_t*>(Wm);
+  lyco::dora_reduce_kernel<1><<<rgrid, 256, 0, stream>>>(dW, wm, t, N, K, on_out, taps, w_dtype);
+  const int64_t total = static_cast<int64_t>(N) * K;
+  int64_t grid = (total + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(di.sms) * 16;
+  if (grid > cap) grid = cap;
+  if (grid * 256 < groups) grid = (groups + 255) / 256;  // the first `groups` threads also write g_scale
+  lyco::dora_apply_bwd_kernel<<<static_cast<int>(grid), 256, 0, stream>>>(dW, wm, sumsq, dora_scale, t, g_scale, N, K, on_out,
+                                                                         taps, mult, eps, w_dtype, groups);
+  LYCO_CUDA(cudaGetLastError());
+  g_launches.fetch_add(2, std::memory_order_relaxed);
   return 0;
 }
 

@@ -31,7 +31,13 @@ EXPORTED_SYMBOLS = (
     "lyco_merge_weight",
     "lyco_factor_grads",
     "lyco_grad_prep",
+    "lyco_lokr_mix",
+    "lyco_lokr_w1grad",
+    "lyco_delta_weight",
+    "lyco_dora_fwd",
+    "lyco_dora_bwd",
 )
+ABI_VERSION = 3
 
 
 class EngineUnavailable(RuntimeError):
@@ -112,6 +118,26 @@ def _bind(lib):
     ]
     lib.lyco_grad_prep.restype = c_int
     lib.lyco_grad_prep.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_int, c_void_p]
+    lib.lyco_lokr_mix.restype = c_int
+    lib.lyco_lokr_mix.argtypes = [
+        c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,  # in out w w_dtype ldw transpose
+        c_int64, c_int, c_int, c_int, c_int, c_void_p,  # M na nb nc dtype stream
+    ]
+    lib.lyco_lokr_w1grad.restype = c_int
+    lib.lyco_lokr_w1grad.argtypes = [
+        c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_float, c_int, c_void_p,
+    ]
+    lib.lyco_delta_weight.restype = c_int
+    lib.lyco_delta_weight.argtypes = [POINTER(DeltaDesc), c_void_p, c_void_p, c_int, c_void_p, c_void_p]
+    lib.lyco_dora_fwd.restype = c_int
+    lib.lyco_dora_fwd.argtypes = [
+        c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_void_p,
+    ]
+    lib.lyco_dora_bwd.restype = c_int
+    lib.lyco_dora_bwd.argtypes = [
+        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,  # dW Wm dora_scale sumsq t g_scale
+        c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_void_p,
+    ]
     return lib
 
 
@@ -131,7 +157,7 @@ def load():
     except OSError as e:  # pragma: no cover - depends on the box
         raise EngineUnavailable(f"lycoris_b200: cannot load {LIB_PATH}: {e}") from e
     _lib = _bind(lib)
-    if _lib.lyco_abi_version() != 2:
+    if _lib.lyco_abi_version() != ABI_VERSION:
         raise EngineUnavailable("lycoris_b200: ABI version mismatch between _lib.py and the .so")
     return _lib
 

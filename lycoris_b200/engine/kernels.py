@@ -281,7 +281,73 @@ def grad_prep(dW: torch.Tensor, P, gscale: float, dtype: torch.dtype) -> torch.T
     return G
 
 
+def lokr_mix(x, w1, na, nb, nc, transpose):
+    """``out[m, a, c] = sum_b Wm(a, b) * x[m, b, c]`` with ``Wm = w1`` (or ``w1ᵀ``); ``x`` is a contiguous 16-bit
+    ``[M, nb*nc]`` array, the result ``[M, na*nc]`` (lyco_lokr_mix)."""
+    _require_cuda(x, w1)
+    M = x.shape[0]
+    assert x.is_contiguous() and x.shape[1] == nb * nc and w1.is_contiguous()
+    out = torch.empty((M, na * nc), device=x.device, dtype=x.dtype)
+    rc = _lib.load().lyco_lokr_mix(_ptr(x), _ptr(out), _ptr(w1), dtype_code(w1.dtype), w1.stride(0), int(transpose),
+                                   M, na, nb, nc, dtype_code(x.dtype), _stream())
+    _lib.check(rc, "lokr_mix")
+    return out
+
+
+def lokr_w1grad(P, R, na, nb, nc, gscale):
+    """fp32 ``g[a, b] = gscale * sum_{m,c} P[m, a, c] * R[m, b, c]`` (lyco_lokr_w1grad)."""
+    _require_cuda(P, R)
+    M = P.shape[0]
+    assert P.is_contiguous() and R.is_contiguous() and P.shape[1] == na * nc and R.shape[1] == nb * nc and R.shape[0] == M
+    g = torch.empty((na, nb), device=P.device, dtype=torch.float32)
+    rc = _lib.load().lyco_lokr_w1grad(_ptr(P), _ptr(R), _ptr(g), M, na, nb, nc, float(gscale), dtype_code(P.dtype),
+                                      _stream())
+    _lib.check(rc, "lokr_w1grad")
+    return g
+
+
+def delta_weight(desc: DeltaDesc, shape, out_dtype=torch.float32, W=None, want_out=True, want_norm=False):
+    """``(dW, norm_sq)``: the adapter's delta weight in ``out_dtype`` (None when ``want_out`` is False) and the fp32
+    0-d tensor ``sum dW^2`` (None unless ``want_norm``) — lyco_delta_weight."""
+    out = torch.empty(shape, device=torch.device("cuda", torch.cuda.current_device()), dtype=out_dtype) if want_out else None
+    dev = out.device if out is not None else torch.device("cuda", torch.cuda.current_device())
+    nsq = torch.zeros((), device=dev, dtype=torch.float32) if want_norm else None
+    rc = _lib.load().lyco_delta_weight(ctypes.byref(desc), _ptr(W), _ptr(out), dtype_code(out_dtype), _ptr(nsq), _stream())
+    _lib.check(rc, "delta_weight")
+    return out, nsq
+
+
+def dora_fwd(Wm, dora_scale, on_out, taps, mult, eps):
+    """``(W'', sumsq)`` — DoRA rescale of the merged 16-bit weight (lyco_dora_fwd)."""
+    _require_cuda(Wm, dora_scale)
+    N = Wm.shape[0]
+    K = Wm.numel() // N
+    groups = N if on_out else K // taps
+    assert Wm.is_contiguous() and dora_scale.dtype == torch.float32 and dora_scale.numel() == groups
+    out = torch.empty_like(Wm)
+    sumsq = torch.empty(groups, device=Wm.device, dtype=torch.float32)
+    rc = _lib.load().lyco_dora_fwd(_ptr(Wm), _ptr(out), _ptr(dora_scale), _ptr(sumsq), N, K, int(on_out), int(taps),
+                                   float(mult), float(eps), dtype_code(Wm.dtype), _stream())
+    _lib.check(rc, "dora_fwd")
+    return out, sumsq
+
+
+def dora_bwd(dW, Wm, dora_scale, sumsq, on_out, taps, mult, eps, want_scale_grad=True):
+    """In place: fp32 ``dW`` (gradient of W'') becomes the gradient of Wm; returns the fp32 gradient of dora_scale."""
+    _require_cuda(dW, Wm)
+    N = Wm.shape[0]
+    K = Wm.numel() // N
+    groups = sumsq.numel()
+    assert dW.dtype == torch.float32 and dW.is_contiguous() and dW.numel() == Wm.numel()
+    t = torch.empty(groups, device=dW.device, dtype=torch.float32)
+    g = torch.empty(groups, device=dW.device, dtype=torch.float32) if want_scale_grad else None
+    rc = _lib.load().lyco_dora_bwd(_ptr(dW), _ptr(Wm), _ptr(dora_scale), _ptr(sumsq), _ptr(t), _ptr(g), N, K, int(on_out),
+                                   int(taps), float(mult), float(eps), dtype_code(Wm.dtype), _stream())
+    _lib.check(rc, "dora_bwd")
+    return g
+
+
 __all__ = [
     "gemm", "gemm_supported", "conv2d_supported", "as_nhwc", "conv2d_fprop", "conv2d_wgrad", "make_desc", "merge_weight", "factor_grads", "dtype_code",
-    "grad_prep", "ALGO_LOCON", "ALGO_LOHA", "ALGO_LOKR", "ALGO_IA3", "ALGO_DYLORA", "ALGO_RAW", "BF16", "F16", "F32",
+    "grad_prep", "lokr_mix", "lokr_w1grad", "delta_weight", "dora_fwd", "dora_bwd", "ALGO_LOCON", "ALGO_LOHA", "ALGO_LOKR", "ALGO_IA3", "ALGO_DYLORA", "ALGO_RAW", "BF16", "F16", "F32",
 ]

@@ -45,6 +45,9 @@ class NativeSpec:
     m_post1: float = 1.0
     m_post2: float = 1.0
     grad_mask: tuple = field(default_factory=tuple)  # optional per-factor "needs grad" override
+    # DoRA (dora_wd): (dora_scale parameter, wd_on_out, multiplier) — the merged weight is rescaled by lyco_dora_fwd;
+    # the merge itself then runs WITHOUT the multiplier (m_post2 = 1), which DoRA applies to the scale instead
+    dora: tuple = None
 
 
 def _autocast_dtype():
@@ -274,21 +277,77 @@ def _lowrank_grads(spec, factors, dWm, prod):
             K.gemm(G2, f[3], out_dtype=f32), K.gemm(f[2], G2, a_mn=True, b_mn=True, out_dtype=f32)]
 
 
+# ------------------------------------------------------- structured LoKr factor gradients
+# dW = kron(w1, w2): g_w1 / g_w2 from two skinny contractions (1/uq of the dense FLOPs each) instead of the dense
+# fp32 dW' = dYᵀ·X + a reduction pass over it (lokr_struct_kernels.cuh).  LYCO_LOKR_GRAD=dense keeps the round-1 path.
+_LOKR_STRUCT = os.environ.get("LYCO_LOKR_GRAD", "structured") != "dense"
+
+
+def _lokr_structured_ok(spec, conv, x2, dy2):
+    return (_LOKR_STRUCT and spec.algo == K.ALGO_LOKR and conv is None and spec.dora is None
+            and 1 <= spec.up <= 8 and 1 <= spec.uq <= 8 and spec.vp % 8 == 0 and spec.vq % 8 == 0
+            and x2.shape[0] > 0 and x2.dtype in _HALF and dy2.dtype == x2.dtype
+            and x2.is_contiguous() and dy2.is_contiguous() and x2.data_ptr() % 16 == 0 and dy2.data_ptr() % 16 == 0)
+
+
+def _lokr_structured_grads(spec, factors, dy2, x2):
+    """[g_w1, g_w2] (fp32) for dW = kron(w1 [up,uq], w2 [vp,vq]) from dY [M, up*vp] and X [M, uq*vq]."""
+    w1, w2 = factors
+    up, uq, vp, vq = spec.up, spec.uq, spec.vp, spec.vq
+    M = x2.shape[0]
+    cdt = x2.dtype
+    gscale = spec.m_pre * spec.m_post1 * spec.m_post2
+    w2c = w2 if w2.dtype == cdt else w2.to(cdt)
+    f32 = torch.float32
+    if up * vq <= uq * vp:
+        # mix the (smaller) input side:  Xt[m,pu,v] = sum_u w1[pu,u] X[m,u,v]
+        Xt = K.lokr_mix(x2, w1, up, uq, vq, transpose=False)
+        dY2 = dy2.view(M * up, vp)
+        g_w2 = K.gemm(dY2, Xt.view(M * up, vq), a_mn=True, b_mn=True, out_dtype=f32)     # [vp, vq]
+        Q = K.gemm(dY2, w2c.t().contiguous())                                            # dY2 · w2   [M*up, vq]
+        g_w1 = K.lokr_w1grad(Q.view(M, up * vq), x2, up, uq, vq, gscale)
+    else:
+        # mix the output-gradient side:  Z[m,u,pv] = sum_pu w1[pu,u] dY[m,pu,pv]
+        Z = K.lokr_mix(dy2, w1, uq, up, vp, transpose=True)
+        X2 = x2.view(M * uq, vq)
+        g_w2 = K.gemm(Z.view(M * uq, vp), X2, a_mn=True, b_mn=True, out_dtype=f32)       # [vp, vq]
+        H = K.gemm(X2, w2c.contiguous())                                                 # X2 · w2ᵀ   [M*uq, vp]
+        g_w1 = K.lokr_w1grad(dy2, H.view(M, uq * vp), up, uq, vp, gscale)
+    if gscale != 1.0:
+        g_w2 = g_w2 * gscale
+    return [g_w1, g_w2]
+
+
 # ------------------------------------------------------------------ autograd nodes
 class _AdapterContraction(torch.autograd.Function):
     """y = op(x, merge(W, factors), bias) with everything on the sm_100a kernels."""
 
     @staticmethod
-    def forward(ctx, x, W, bias, spec, conv, delta_only, ac_dtype, *factors):
+    def _merge(spec, factors_u, W, ac_dtype, out_dim, in_dim):
+        prod = _lowrank_tc_dtype(spec, factors_u, out_dim, in_dim, ac_dtype)
+        if prod is not None:
+            return _lowrank_merge(spec, factors_u, W, prod, out_dim, in_dim)
+        return K.merge_weight(_build_desc(spec, factors_u, W.dtype, ac_dtype, out_dim, in_dim), W)
+
+    @staticmethod
+    def _dora_args(spec, W):
+        g, on_out, mult = spec.dora
+        taps = 1
+        for d_ in W.shape[2:]:
+            taps *= d_
+        # eps is that of the dtype the reference computes the norm in (= dora_scale's: fp32, or bf16 for a bf16 adapter)
+        return g.detach().reshape(-1).float().contiguous(), bool(on_out), taps, float(mult), float(torch.finfo(g.dtype).eps)
+
+    @staticmethod
+    def forward(ctx, x, W, bias, spec, conv, delta_only, ac_dtype, dora_scale, *factors):
         factors_u = _uniform_factors(factors)
         out_dim = W.shape[0]
         in_dim = W.numel() // out_dim
-        prod = _lowrank_tc_dtype(spec, factors_u, out_dim, in_dim, ac_dtype)
-        if prod is not None:
-            Wm = _lowrank_merge(spec, factors_u, W, prod, out_dim, in_dim)
-        else:
-            desc = _build_desc(spec, factors_u, W.dtype, ac_dtype, out_dim, in_dim)
-            Wm = K.merge_weight(desc, W)
+        Wm = _AdapterContraction._merge(spec, factors_u, W, ac_dtype, out_dim, in_dim)
+        sumsq = None
+        if spec.dora is not None:
+            g32, on_out, taps, mult, eps = _AdapterContraction._dora_args(spec, W)
+            Wm, sumsq = K.dora_fwd(Wm, g32, on_out, taps, mult, eps)  # the pre-rescale W + dW is recomputed in backward
         if delta_only:
             Wm = Wm - W  # exact on W's grid: this is the reference's `new_weight - base_weight`
         if conv is None:
@@ -298,20 +357,22 @@ class _AdapterContraction(torch.autograd.Function):
             y = _dense_nt(x2, Wm, bias).view(*x.shape[:-1], out_dim)
         else:
             y, x, ctx.conv_info = _conv_forward(x, Wm, bias, conv)
-        ctx.save_for_backward(x, W, Wm, *factors)
+        ctx.save_for_backward(x, W, Wm, sumsq, *factors)
         ctx.spec, ctx.conv, ctx.ac_dtype = spec, conv, ac_dtype
         ctx.dims = (out_dim, in_dim)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, W, Wm, *factors = ctx.saved_tensors
+        x, W, Wm, sumsq, *factors = ctx.saved_tensors
         spec, conv = ctx.spec, ctx.conv
         out_dim, in_dim = ctx.dims
+        NF = 8  # index of the first factor among forward's arguments
         need_x = ctx.needs_input_grad[0]
-        need_f = any(ctx.needs_input_grad[7:])
+        need_f = any(ctx.needs_input_grad[NF:]) or ctx.needs_input_grad[NF - 1]
         dx = None
         dWm = None
+        gs = None
         if conv is None:
             dy2 = dy.reshape(-1, out_dim)
             if not dy2.is_contiguous():
@@ -322,24 +383,39 @@ class _AdapterContraction(torch.autograd.Function):
                 x2 = x.reshape(-1, x.shape[-1])
                 if not x2.is_contiguous():
                     x2 = x2.contiguous()
-                dWm = _dense_tn_f32(dy2, x2)
+                if _lokr_structured_ok(spec, conv, x2, dy2):
+                    gs = _lokr_structured_grads(spec, _uniform_factors(factors), dy2, x2)
+                else:
+                    dWm = _dense_tn_f32(dy2, x2)
         else:
             dx, dw = _conv_backward(dy, x, Wm, conv, ctx.conv_info, need_x, need_f)
             if need_f:
                 dWm = dw.reshape(out_dim, in_dim).float()
         grads = [None] * len(factors)
+        g_dora = None
         if need_f:
             factors_u = _uniform_factors(factors)
-            prod = _lowrank_tc_dtype(spec, factors_u, out_dim, in_dim, ctx.ac_dtype)
-            if prod is not None:
-                gs = _lowrank_grads(spec, factors_u, dWm.contiguous(), prod)
-            else:
-                desc = _build_desc(spec, factors_u, W.dtype, ctx.ac_dtype, out_dim, in_dim)
-                gs = K.factor_grads(desc, dWm.contiguous(), W, [f.shape for f in factors_u])
+            if gs is None:
+                dWm = dWm.contiguous()
+                if spec.dora is not None:
+                    # gradient of W'' -> gradient of W + dW (in place) and of dora_scale
+                    g32, on_out, taps, mult, eps = _AdapterContraction._dora_args(spec, W)
+                    Wpre = _AdapterContraction._merge(spec, factors_u, W, ctx.ac_dtype, out_dim, in_dim)
+                    g_dora = K.dora_bwd(dWm, Wpre, g32, sumsq, on_out, taps, mult, eps,
+                                        want_scale_grad=ctx.needs_input_grad[NF - 1])
+                    if g_dora is not None:
+                        ds = spec.dora[0]
+                        g_dora = g_dora.view(ds.shape).to(ds.dtype)
+                prod = _lowrank_tc_dtype(spec, factors_u, out_dim, in_dim, ctx.ac_dtype)
+                if prod is not None:
+                    gs = _lowrank_grads(spec, factors_u, dWm, prod)
+                else:
+                    desc = _build_desc(spec, factors_u, W.dtype, ctx.ac_dtype, out_dim, in_dim)
+                    gs = K.factor_grads(desc, dWm, W, [f.shape for f in factors_u])
             for i, (g, f) in enumerate(zip(gs, factors)):
-                if ctx.needs_input_grad[7 + i]:
+                if ctx.needs_input_grad[NF + i]:
                     grads[i] = g.to(f.dtype) if g.dtype != f.dtype else g
-        return (dx, None, None, None, None, None, None, *grads)
+        return (dx, None, None, None, None, None, None, g_dora, *grads)
 
 
 class _MergedContraction(torch.autograd.Function):
@@ -381,6 +457,27 @@ class _MergedContraction(torch.autograd.Function):
             if dw is not None and dw.dtype != Wm.dtype:
                 dw = dw.to(Wm.dtype)
         return dx, dw, None, None
+
+
+# ------------------------------------------------------------------- cold paths
+def delta_weight(spec, m_pre, m_post1, m_post2, shape, want_out=True, want_norm=False):
+    """``(dW, sum dW^2)`` of one adapter through lyco_delta_weight, in the FACTOR dtype with the rounding points of
+    the reference's get_diff_weight / get_weight (torch ops in the parameter dtype): merge_to, onfly_merge,
+    apply_max_norm (reference base.py:326-374, lokr.py:383-397, 442-466) without assembling kron / up@down / the
+    Hadamard product with PyTorch ops.  The multipliers replace the training chain's (m_pre, m_post1, m_post2)."""
+    factors = _uniform_factors(tuple(f.detach() for f in spec.factors))
+    fdt = factors[0].dtype
+    out_dim = shape[0]
+    in_dim = 1
+    for d_ in shape[1:]:
+        in_dim *= d_
+    half = fdt in _HALF
+    desc = K.make_desc(
+        spec.algo, out_dim, in_dim, factors=factors, w_dtype=fdt, rank=spec.rank, up=spec.up, uq=spec.uq, vp=spec.vp,
+        vq=spec.vq, on_input=spec.on_input, ia3_group=spec.ia3_group, pre_round=int(half), pre_dtype=fdt,
+        m_in=spec.m_in, m_pre=m_pre, m_post1=m_post1, m_post2=m_post2)
+    with torch.cuda.device(factors[0].device):
+        return K.delta_weight(desc, tuple(shape), fdt, None, want_out, want_norm)
 
 
 # --------------------------------------------------------------------- dispatcher
@@ -454,7 +551,8 @@ def adapter_forward(module, x, args, kwargs, native_spec, assemble_fallback):
 
     spec = native_spec()
     if spec is not None:
-        y = _AdapterContraction.apply(x, W, None if not plain else bias, spec, conv, not plain, ac, *spec.factors)
+        y = _AdapterContraction.apply(x, W, None if not plain else bias, spec, conv, not plain, ac,
+                                      spec.dora[0] if spec.dora is not None else None, *spec.factors)
     else:
         Wm = assemble_fallback(W)
         if not plain:
@@ -494,7 +592,8 @@ def adapter_forward_pointwise(module, x, W, bias, ac, native_spec, assemble_fall
     W2 = W.reshape(W.shape[0], C)
     spec = native_spec()
     if spec is not None:
-        y2 = _AdapterContraction.apply(x2, W2, bias if plain else None, spec, None, not plain, ac, *spec.factors)
+        y2 = _AdapterContraction.apply(x2, W2, bias if plain else None, spec, None, not plain, ac,
+                                       spec.dora[0] if spec.dora is not None else None, *spec.factors)
     else:
         Wm = assemble_fallback(W).reshape(W.shape[0], C)
         if not plain:

@@ -426,6 +426,21 @@ class LycorisBaseModule(ModuleCustomSD):
             drop /= drop.mean()
         return weight * drop
 
+    def _delta_via_engine(self, m_pre, m_post1, m_post2=1.0, shape=None, want_out=True, want_norm=False):
+        """``(dW, sum dW^2)`` through the weight-side CUDA kernel (lyco_delta_weight) when this adapter lives on a
+        CUDA device and its factors are in the kernel's scope; ``None`` otherwise (CPU tensors, Tucker cores, a
+        trainable scalar, rank dropout in training mode: the host PyTorch path, as upstream)."""
+        first = next(iter(self.parameters()), None)
+        if first is None or not first.is_cuda or not hasattr(self, "_native_spec"):
+            return None
+        spec = self._native_spec()
+        if spec is None:
+            return None
+        from ..engine import ops
+
+        return ops.delta_weight(spec, float(m_pre), float(m_post1), float(m_post2), tuple(shape or self.shape),
+                                want_out, want_norm)
+
     def _fused(self, x, args, kwargs, native_spec, assemble_fallback):
         """Dispatch the rebuild-mode forward to the engine.
 

@@ -147,7 +147,9 @@ class LoConModule(LycorisBaseModule):
         return weight * self.scalar.to(device)
 
     def get_diff_weight(self, multiplier=1, shape=None, device=None):
-        diff = self.make_weight(device=device) * (self.scale * multiplier)
+        cold = self.tucker or isinstance(self.scalar, nn.Parameter)  # outside the delta kernel's scope: host ops
+        eng = None if cold else self._delta_via_engine(self._scalar_host(), self.scale * multiplier)
+        diff = eng[0] if eng is not None else self.make_weight(device=device) * (self.scale * multiplier)
         if shape is not None:
             diff = diff.view(shape)
         if device is not None:
@@ -163,7 +165,12 @@ class LoConModule(LycorisBaseModule):
 
     @torch.no_grad()
     def apply_max_norm(self, max_norm, device=None):
-        orig_norm = self.make_weight(device).norm() * self.scale
+        cold = self.tucker or isinstance(self.scalar, nn.Parameter)
+        eng = None if cold else self._delta_via_engine(self._scalar_host(), self.scale, want_out=False, want_norm=True)
+        if eng is not None:
+            orig_norm = eng[1].sqrt().to(self.lora_up.weight.dtype)  # ||dW||_F reduced inside the delta kernel
+        else:
+            orig_norm = self.make_weight(device).norm() * self.scale
         norm = torch.clamp(orig_norm, max_norm / 2)
         desired = torch.clamp(norm, max=max_norm)
         ratio = desired.cpu() / norm.cpu()
@@ -194,7 +201,7 @@ class LoConModule(LycorisBaseModule):
         from ..engine.ops import NativeSpec
         from ..engine.kernels import ALGO_LOCON
 
-        if self.tucker or self.wd or isinstance(self.scalar, nn.Parameter) or (self.training and self.rank_dropout):
+        if self.tucker or isinstance(self.scalar, nn.Parameter) or (self.training and self.rank_dropout):
             return None
         up, down = self.lora_up.weight, self.lora_down.weight
         return NativeSpec(
@@ -203,7 +210,8 @@ class LoConModule(LycorisBaseModule):
             rank=self.lora_dim,
             m_pre=self._scalar_host(),
             m_post1=float(self.scale),
-            m_post2=float(self.multiplier),
+            m_post2=1.0 if self.wd else float(self.multiplier),
+            dora=(self.dora_scale, self.wd_on_out, float(self.multiplier)) if self.wd else None,
         )
 
     def _assemble(self, base_weight):

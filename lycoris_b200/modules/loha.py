@@ -136,7 +136,8 @@ class LohaModule(LycorisBaseModule):
     def get_diff_weight(self, multiplier=1, shape=None, device=None):
         # NB: like the reference (loha.py:229-230) this applies `scale` on top of get_weight, which
         # already carries it — merge_to therefore differs from the training forward by 1/scale.
-        diff = self.get_weight(shape) * (self.scale * multiplier)
+        eng = self._delta_via_engine(self.scale, self.scale * multiplier, shape=shape)
+        diff = eng[0] if eng is not None else self.get_weight(shape) * (self.scale * multiplier)
         if device is not None:
             diff = diff.to(device)
         return diff, None
@@ -150,7 +151,12 @@ class LohaModule(LycorisBaseModule):
 
     @torch.no_grad()
     def apply_max_norm(self, max_norm, device=None):
-        orig_norm = (self.get_weight(self.shape) * self.scalar).norm()
+        cold = self.tucker or isinstance(self.scalar, nn.Parameter)
+        eng = None if cold else self._delta_via_engine(self.scale, self._scalar_host(), want_out=False, want_norm=True)
+        if eng is not None:
+            orig_norm = eng[1].sqrt().to(self.hada_w1_a.dtype)  # ||dW||_F reduced inside the delta kernel
+        else:
+            orig_norm = (self.get_weight(self.shape) * self.scalar).norm()
         norm = torch.clamp(orig_norm, max_norm / 2)
         desired = torch.clamp(norm, max=max_norm)
         ratio = desired.cpu() / norm.cpu()
@@ -174,7 +180,7 @@ class LohaModule(LycorisBaseModule):
         from ..engine.kernels import ALGO_LOHA
         from ..engine.ops import NativeSpec
 
-        if self.tucker or self.wd or isinstance(self.scalar, nn.Parameter) or (self.training and self.rank_dropout):
+        if self.tucker or isinstance(self.scalar, nn.Parameter) or (self.training and self.rank_dropout):
             return None
         return NativeSpec(
             algo=ALGO_LOHA,
@@ -182,7 +188,8 @@ class LohaModule(LycorisBaseModule):
             rank=self.lora_dim,
             m_pre=float(self.scale),
             m_post1=self._scalar_host(),
-            m_post2=float(self.multiplier),
+            m_post2=1.0 if self.wd else float(self.multiplier),
+            dora=(self.dora_scale, self.wd_on_out, float(self.multiplier)) if self.wd else None,
         )
 
     def _assemble(self, base_weight):

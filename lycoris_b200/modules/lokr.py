@@ -240,7 +240,8 @@ class LokrModule(LycorisBaseModule):
 
     def get_diff_weight(self, multiplier=1, shape=None, device=None):
         # NB: like the reference (lokr.py:384-385) `scale` is applied again on top of get_weight.
-        diff = self.get_weight(shape) * (self.scale * multiplier)
+        eng = self._delta_via_engine(self.scale, self.scale * multiplier, shape=shape)
+        diff = eng[0] if eng is not None else self.get_weight(shape) * (self.scale * multiplier)
         if device is not None:
             diff = diff.to(device)
         return diff, None
@@ -254,7 +255,11 @@ class LokrModule(LycorisBaseModule):
 
     @torch.no_grad()
     def apply_max_norm(self, max_norm, device=None):
-        orig_norm = self.get_weight(self.shape).norm()
+        eng = self._delta_via_engine(self.scale, 1.0, want_out=False, want_norm=True)
+        if eng is not None:
+            orig_norm = eng[1].sqrt().to(self._w1().dtype)  # ||kron(w1, w2) * scale||_F without forming the product
+        else:
+            orig_norm = self.get_weight(self.shape).norm()
         norm = torch.clamp(orig_norm, max_norm / 2)
         desired = torch.clamp(norm, max=max_norm)
         ratio = desired.cpu() / norm.cpu()
@@ -314,7 +319,7 @@ class LokrModule(LycorisBaseModule):
         from ..engine.kernels import ALGO_LOKR
         from ..engine.ops import NativeSpec
 
-        if self.tucker or self.wd or isinstance(self.scalar, nn.Parameter) or (self.training and self.rank_dropout):
+        if self.tucker or isinstance(self.scalar, nn.Parameter) or (self.training and self.rank_dropout):
             return None
         # inner low-rank products are tiny (e.g. 160x4 @ 4x160): formed by PyTorch, with autograd
         # carrying g_w2 back to w2_a / w2_b; the kernels see the two Kronecker blocks only.
@@ -327,7 +332,8 @@ class LokrModule(LycorisBaseModule):
             matmul_product=False,  # torch.kron is not an autocast op: the product keeps the factor dtype
             m_pre=float(self.scale),
             m_post1=self._scalar_host(),
-            m_post2=float(self.multiplier),
+            m_post2=1.0 if self.wd else float(self.multiplier),
+            dora=(self.dora_scale, self.wd_on_out, float(self.multiplier)) if self.wd else None,
         )
 
     def _assemble(self, base_weight):

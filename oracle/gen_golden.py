@@ -38,7 +38,11 @@ LAYERS = {
     "conv3": dict(kind="conv", in_dim=16, out_dim=32, k=3, stride=1, pad=1, x=(2, 16, 8, 8)),
     "conv1": dict(kind="conv", in_dim=32, out_dim=16, k=1, stride=1, pad=0, x=(2, 32, 6, 6)),
     "conv3s2": dict(kind="conv", in_dim=16, out_dim=16, k=3, stride=2, pad=1, x=(2, 16, 8, 8)),
+    # 64 input channels: TMA-im2col addressable, so the engine runs these on conv_sm100_kernel (round-2 fixtures,
+    # written by oracle/gen_golden_tucker.py; not part of the layers_* / options_* loops below)
+    "conv3c64": dict(kind="conv", in_dim=64, out_dim=64, k=3, stride=1, pad=1, x=(2, 64, 8, 8)),
 }
+ROUND1_LAYERS = ("linear", "conv3", "conv1", "conv3s2")
 ALGOS = {
     "locon": dict(cls="LoConModule", dim=4, alpha=2.0, kw={}),
     "loha": dict(cls="LohaModule", dim=4, alpha=2.0, kw={}),
@@ -91,7 +95,7 @@ def oracle_inputs(algo_key, module):
         p = {"lora_up.weight": sd["lora_up.weight"], "lora_down.weight": sd["lora_down.weight"]}
         cfg["scale"] = module.scale
         return "locon", p, cfg
-    if algo_key == "loha":
+    if algo_key.startswith("loha"):
         p = {k: sd[k] for k in ("hada_w1_a", "hada_w1_b", "hada_w2_a", "hada_w2_b")}
         cfg["scale"] = module.scale
         return "loha", p, cfg
@@ -153,7 +157,7 @@ def run_case(algo_key, layer_key, regime, seed, extra_kw=None, multiplier=1.0, u
     algo, p, cfg = oracle_inputs(algo_key, mod)
     cfg["multiplier"] = multiplier
     cfg["wd_on_out"] = getattr(mod, "wd_on_out", True)
-    for extra in ("scalar", "dora_scale", "lora_mid.weight"):
+    for extra in ("scalar", "dora_scale", "lora_mid.weight", "hada_t1", "hada_t2"):
         named = dict(mod.named_parameters())
         if extra in named:
             p[extra] = named[extra]
@@ -260,7 +264,7 @@ def main():
         cases = {}
         seed = 100
         for algo_key in ALGOS:
-            for layer_key in LAYERS:
+            for layer_key in ROUND1_LAYERS:
                 seed += 10
                 cases[f"{algo_key}/{layer_key}"] = run_case(algo_key, layer_key, regime, seed)
                 n += 1

@@ -132,18 +132,63 @@ class _HadaWeight(torch.autograd.Function):
         return grad_w1d, grad_w1u, grad_w2d, grad_w2u, None
 
 
+_TUCKER_FWD = "i j ..., j r, i p -> p r ..."  # core [r, r, *k], down [r, in], up [r, out] -> [out, in, *k]
+
+
+class _HadaWeightTucker(torch.autograd.Function):
+    """lycoris/functional/loha.py:33-75: Hadamard product of two Tucker rebuilds.  As with _HadaWeight the custom
+    backward runs outside autocast, and its contraction ORDER (core x down first, then x up; gradients peeled off
+    in the order up -> down -> core) fixes the rounding, so it is restated contraction by contraction."""
+
+    @staticmethod
+    def forward(ctx, t1, w1d, w1u, t2, w2d, w2u, scale):
+        ctx.save_for_backward(t1, w1d, w1u, t2, w2d, w2u, scale)
+        return torch.einsum(_TUCKER_FWD, t1, w1d, w1u) * torch.einsum(_TUCKER_FWD, t2, w2d, w2u) * scale  # loha.py:38-41
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        t1, w1d, w1u, t2, w2d, w2u, scale = ctx.saved_tensors
+        grad_out = grad_out * scale  # loha.py:46
+        # NB the reference reuses `temp` = (t2 x w2d) — the OTHER branch's half product — when it forms grad_w1u
+        # (loha.py:48,54), and (t1 x w1d) for grad_w2u (loha.py:62,68).  That is what is restated here.
+        half2 = torch.einsum("i j ..., j r -> i r ...", t2, w2d)
+        gw1 = torch.einsum("i j ..., i r -> r j ...", half2, w2u) * grad_out
+        g_w1u = torch.einsum("r j ..., i j ... -> r i", half2, gw1)
+        g_half = torch.einsum("i j ..., i r -> r j ...", gw1, w1u.T)
+        g_w1d = torch.einsum("i r ..., i j ... -> r j", t1, g_half)
+        g_t1 = torch.einsum("i j ..., j r -> i r ...", g_half, w1d.T)
+        half1 = torch.einsum("i j ..., j r -> i r ...", t1, w1d)
+        gw2 = torch.einsum("i j ..., i r -> r j ...", half1, w1u) * grad_out
+        g_w2u = torch.einsum("r j ..., i j ... -> r i", half1, gw2)
+        g_half = torch.einsum("i j ..., i r -> r j ...", gw2, w2u.T)
+        g_w2d = torch.einsum("i r ..., i j ... -> r j", t2, g_half)
+        g_t2 = torch.einsum("i j ..., j r -> i r ...", g_half, w2d.T)
+        return g_t1, g_w1d, g_w1u, g_t2, g_w2d, g_w2u, None
+
+
 def delta_loha(p, shape, cfg):
     """lycoris/modules/loha.py:194-226 get_weight -> functional/loha.py:119-147 diff_weight ->
-    HadaWeight; scale is a 0-dim tensor in the factor dtype (loha.py:195-197)."""
+    HadaWeight (or HadaWeightTucker when the Tucker cores hada_t1 / hada_t2 exist); scale is a 0-dim tensor in the
+    factor dtype (loha.py:195-197)."""
     gamma = torch.tensor(cfg["scale"], dtype=p["hada_w1_b"].dtype, device=p["hada_w1_b"].device)
-    w = _HadaWeight.apply(p["hada_w1_b"], p["hada_w1_a"], p["hada_w2_b"], p["hada_w2_a"], gamma)
+    if "hada_t1" in p:
+        w = _HadaWeightTucker.apply(p["hada_t1"], p["hada_w1_b"], p["hada_w1_a"], p["hada_t2"], p["hada_w2_b"],
+                                    p["hada_w2_a"], gamma)
+    else:
+        w = _HadaWeight.apply(p["hada_w1_b"], p["hada_w1_a"], p["hada_w2_b"], p["hada_w2_a"], gamma)
     return w.reshape(shape)
 
 
 def delta_lokr(p, shape, cfg):
     """lycoris/modules/lokr.py:358-381 get_weight -> functional/lokr.py:11-20 make_kron."""
     w1 = p["lokr_w1"] if "lokr_w1" in p else p["lokr_w1_a"] @ p["lokr_w1_b"]
-    w2 = p["lokr_w2"] if "lokr_w2" in p else p["lokr_w2_a"] @ p["lokr_w2_b"]
+    if "lokr_w2" in p:
+        w2 = p["lokr_w2"]
+    elif "lokr_t2" in p:
+        # Tucker core for the large block (lokr.py:121-128, 362-366): rebuild_tucker(t2, w2_a, w2_b)
+        w2 = torch.einsum("i j ..., i p, j r -> p r ...", p["lokr_t2"], p["lokr_w2_a"], p["lokr_w2_b"])
+    else:
+        w2 = p["lokr_w2_a"] @ p["lokr_w2_b"]
     for _ in range(w2.dim() - w1.dim()):
         w1 = w1.unsqueeze(-1)
     rebuild = torch.kron(w1, w2.contiguous())

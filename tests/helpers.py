@@ -61,7 +61,7 @@ def oracle_args(case, device="cpu"):
     cfg = {"multiplier": meta.get("multiplier", 1.0), "scale": meta["scale"], "wd_on_out": meta.get("wd_on_out", True)}
     if key == "locon":
         algo = "locon"
-    elif key == "loha":
+    elif key.startswith("loha"):
         algo = "loha"
     elif key.startswith("lokr"):
         algo = "lokr"

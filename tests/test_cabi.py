@@ -24,7 +24,7 @@ def test_header_symbols_are_exported():
     assert sorted(_lib.EXPORTED_SYMBOLS) == declared
     for sym in declared:
         assert hasattr(lib, sym), sym
-    assert lib.lyco_abi_version() == 2
+    assert lib.lyco_abi_version() == 3
 
 
 def test_delta_desc_layout_matches_header():

@@ -419,6 +419,23 @@ def test_engine_option_variants_match_reference_fixtures(regime):
         _check(name, y, dx, grads, case["y"], case["dx"], case["grads"])
 
 
+@pytest.mark.parametrize("regime", ["bf16", "autocast_bf16"])
+def test_engine_tucker_and_64_channel_variants_match_reference_fixtures(regime):
+    """Round-2 fixtures: LoHa-Tucker, LoKr-Tucker, LoCon-Tucker, DoRA (lyco_dora_fwd / lyco_dora_bwd) and plain LoKr.
+    The conv3c64 cases have 64 input channels, so fprop / dgrad / wgrad run on conv_sm100_kernel — an option-variant
+    layer on the engine's own convolution kernels, against outputs of the reference itself."""
+    from lycoris_b200.engine import _lib
+
+    cases = load_cases(regime, "tucker")
+    for name in case_ids(regime, "tucker"):
+        case = cases[name]
+        before = _lib.launch_count()
+        y, dx, grads = _run_engine(case, regime)
+        if name.endswith("conv3c64"):
+            assert _lib.launch_count() >= before + 5, name  # relayouts + fprop + dgrad + wgrad at least
+        _check(name, y, dx, grads, case["y"], case["dx"], case["grads"])
+
+
 def test_conv_engine_with_channel_sliced_gradient_and_input():
     """Non-dense NHWC-looking tensors (channel slices of a concatenation — what torch.cat's backward hands to the
     upsampler convolution of a UNet) must be densified, not passed through: regression test for a layout pass that

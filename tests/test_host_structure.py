@@ -201,3 +201,62 @@ def test_builtin_preset_tables_equal_the_reference():
     with open(os.path.join(GOLDEN, "presets.json")) as fh:
         ref = json.load(fh)
     assert json.loads(json.dumps(PRESET, sort_keys=True)) == ref
+
+
+def test_plain_forward_detection_rejects_foreign_instance_patches():
+    """Round-1 advisor finding: a base layer whose forward was already instance-patched (kohya networks.lora, an
+    accelerate offload hook) must NOT be treated as pristine — the engine would contract org.weight directly and
+    drop the other patch's contribution.  Only the class's own bound forward counts as plain."""
+    import types
+
+    import torch.nn as nn
+
+    import lycoris_b200 as L
+
+    lin = nn.Linear(16, 16)
+    mod = L.LoConModule("a", lin, 1.0, 4, 1)
+    mod.apply_to()
+    assert mod._is_outermost_on_plain_forward()
+    mod.restore()
+
+    lin2 = nn.Linear(16, 16)
+    orig = lin2.forward
+    lin2.forward = lambda x: orig(x) + 1.0  # plain function
+    m2 = L.LoConModule("b", lin2, 1.0, 4, 1)
+    m2.apply_to()
+    assert not m2._is_outermost_on_plain_forward()
+
+    lin3 = nn.Linear(16, 16)
+    lin3.forward = types.MethodType(lambda self, x: nn.Linear.forward(self, x) * 2, lin3)  # bound, but not the class's
+    for cls, kw in ((L.LoConModule, {}), (L.IA3Module, {})):
+        m3 = cls("c", lin3, 1.0, 4, 1, **kw)
+        m3.apply_to()
+        assert not m3._is_outermost_on_plain_forward(), cls.__name__
+        m3.restore()
+
+    # stacking: the second wrapper sits on the first wrapper's forward, not on the class forward
+    lin4 = nn.Linear(16, 16)
+    a, b = L.LoConModule("s1", lin4, 1.0, 4, 1), L.LoConModule("s2", lin4, 1.0, 4, 1)
+    a.apply_to()
+    b.apply_to()
+    assert a._is_outermost_on_plain_forward() and not b._is_outermost_on_plain_forward()
+
+
+def test_out_of_scope_checkpoint_entries_warn_instead_of_loading_silently(caplog):
+    import logging
+
+    import torch
+
+    from lycoris_b200.modules import get_module
+
+    sd = {"lora_unet_x.diff": torch.zeros(2, 2), "lora_unet_y.oft_blocks": torch.zeros(2, 2, 2),
+          "lora_unet_z.lora_up.weight": torch.zeros(4, 2), "lora_unet_z.lora_down.weight": torch.zeros(2, 4)}
+    logging.getLogger("LyCORIS").setLevel(logging.WARNING)
+    with caplog.at_level(logging.WARNING, logger="LyCORIS"):
+        assert get_module(sd, "lora_unet_x") == (None, None)
+        assert get_module(sd, "lora_unet_y") == (None, None)
+        cls, _ = get_module(sd, "lora_unet_z")
+    logging.getLogger("LyCORIS").setLevel(logging.ERROR)
+    assert cls.__name__ == "LoConModule"
+    text = " ".join(r.getMessage() for r in caplog.records)
+    assert "Full adapter" in text and "Diag-OFT/BOFT" in text
