@@ -549,6 +549,13 @@ def run_engine(args):
     print(json.dumps(result), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    ref = result.get("gpu_eager_reference") or {}
+    if ref.get("loss_check") == "FAILED":
+        # the line above is still printed (with loss_check = FAILED); a parity failure at the headline config must not
+        # look like a successful run
+        print(f"[bench] PARITY FAILURE: engine loss {ref['engine_loss']} vs reference loss {ref['loss']} "
+              f"(relative difference {ref['loss_rel_diff']:.3e} > 2e-2)", file=sys.stderr)
+        sys.exit(3)
 
 
 def profile_one_step(args, step):
@@ -677,7 +684,8 @@ def gpu_eager_reference(args, unet, engine_net, static, engine_loss):
             "value": 1000.0 / ms, "unit": "steps/s", "ms_per_step": ms, "steps": n, "warmup": 3,
             "source": "unmodified reference from baseline/_ref (pip install --no-deps --target of /root/reference), "
                       "lycoris.kohya.create_network + apply_to, PyTorch eager, bf16 autocast, same model / parameters / inputs",
-            "loss": ref_loss, "engine_loss": engine_loss, "loss_rel_diff": rel, "loss_check": "ok" if rel <= 2e-2 else "FAILED",
+            "loss": ref_loss, "engine_loss": engine_loss, "loss_rel_diff": rel,
+            "loss_check": "n/a" if engine_loss != engine_loss else ("ok" if rel <= 2e-2 else "FAILED"),
             "state_dict_key_mismatches": n_missing,
         }
         if notes:
@@ -685,7 +693,6 @@ def gpu_eager_reference(args, unet, engine_net, static, engine_loss):
         for lora in list(getattr(net, "loras", [])):
             lora.restore()
         del net
-        assert rel <= 2e-2, f"engine loss {engine_loss} vs reference loss {ref_loss}: relative difference {rel:.3e} > 2e-2"
         return out
     finally:
         torch.cuda.empty_cache()
@@ -718,10 +725,7 @@ def run_reference_gpu(args):
     for k in ("sample", "target"):
         st[k] = st[k].contiguous(memory_format=torch.channels_last)
     args.ref_steps = args.steps
-    try:
-        ref = gpu_eager_reference(args, unet, net, st, float("nan"))
-    except AssertionError:
-        ref = {}
+    ref = gpu_eager_reference(args, unet, net, st, float("nan"))
     print(json.dumps({"metric": f"{cfg.name.upper()}-UNet+{wl['label']} fwd+bwd steps/sec", "impl": "reference-gpu",
                       "value": ref.get("value"), "unit": "steps/s", "ms_per_step": ref.get("ms_per_step"), "n_gpus": 1,
                       "steps": args.steps, "warmup": 3, "dtype": "bf16", "data": "synthetic", "detail": ref,

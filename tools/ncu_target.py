@@ -12,7 +12,7 @@ from lycoris_b200.engine import kernels as k
 def main():
     torch.manual_seed(0)
     reps = int(os.environ.get("REPS", "3"))
-    for (M, N, K) in ((8192, 10240, 1280), (8192, 1280, 1280)):
+    for (M, N, K) in ((8192, 10240, 1280), (8192, 1280, 1280), (8192, 1280, 5120)):
         X = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
         W = (torch.randn(N, K, device="cuda") * 0.03).to(torch.bfloat16)
         b = torch.zeros(N, device="cuda", dtype=torch.bfloat16)
@@ -26,6 +26,22 @@ def main():
             dx = k.gemm(dY, Wm, b_mn=True)
             dw = k.gemm(dY, X, a_mn=True, b_mn=True, out_dtype=torch.float32)
             g = k.factor_grads(d, dw, None, [w1.shape, w2.shape])
+            # round 2: the structured factor gradients that replace `dw` + factor_grads for Linear LoKr layers
+            up = uq = 8
+            vp, vq = N // 8, K // 8
+            w2c = w2.to(torch.bfloat16)
+            if up * vq <= uq * vp:
+                Xt = k.lokr_mix(X, w1, up, uq, vq, False)
+                dY2 = dY.view(M * up, vp)
+                g2 = k.gemm(dY2, Xt.view(M * up, vq), a_mn=True, b_mn=True, out_dtype=torch.float32)
+                Q = k.gemm(dY2, w2c.t().contiguous())
+                g1 = k.lokr_w1grad(Q.view(M, up * vq), X, up, uq, vq, 1.0)
+            else:
+                Z = k.lokr_mix(dY, w1, uq, up, vp, True)
+                X2 = X.view(M * uq, vq)
+                g2 = k.gemm(Z.view(M * uq, vp), X2, a_mn=True, b_mn=True, out_dtype=torch.float32)
+                H = k.gemm(X2, w2c)
+                g1 = k.lokr_w1grad(dY, H.view(M, uq * vp), up, uq, vp, 1.0)
         torch.cuda.synchronize()
     # 3x3 convolution, SDXL 1280-channel block at 32x32 (batch 8): fprop, dgrad (fprop on dY), wgrad
     Nb, C, O, H = 8, 1280, 1280, 32
