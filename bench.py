@@ -684,7 +684,8 @@ def gpu_eager_reference(args, unet, engine_net, static, engine_loss):
             "value": 1000.0 / ms, "unit": "steps/s", "ms_per_step": ms, "steps": n, "warmup": 3,
             "source": "unmodified reference from baseline/_ref (pip install --no-deps --target of /root/reference), "
                       "lycoris.kohya.create_network + apply_to, PyTorch eager, bf16 autocast, same model / parameters / inputs",
-            "loss": ref_loss, "engine_loss": engine_loss, "loss_rel_diff": rel,
+            "loss": ref_loss, "engine_loss": None if engine_loss != engine_loss else engine_loss,
+            "loss_rel_diff": None if rel != rel else rel,
             "loss_check": "n/a" if engine_loss != engine_loss else ("ok" if rel <= 2e-2 else "FAILED"),
             "state_dict_key_mismatches": n_missing,
         }
