@@ -21,6 +21,7 @@ Prints ONE JSON line (rank 0).
 """
 import argparse
 import json
+import logging
 import os
 import statistics
 import subprocess
@@ -175,6 +176,7 @@ def import_reference():
     except Exception as e:  # noqa: BLE001
         return None, f"import failed: {type(e).__name__}: {e}"
     notes = []
+    logging.getLogger("LyCORIS").setLevel(logging.ERROR)
     if "ia3" not in ref_wrapper.network_module_dict:
         # upstream omission (lycoris/wrapper.py:45-55): the class exists but is not registered, so any preset that
         # names algo="ia3" raises KeyError.  Registering the reference's OWN class is the one change made.
@@ -689,7 +691,7 @@ def gpu_eager_reference(args, unet, engine_net, static, engine_loss):
             "loss_check": "n/a" if engine_loss != engine_loss else ("ok" if rel <= 2e-2 else "FAILED"),
             "state_dict_key_mismatches": n_missing,
         }
-        if notes:
+        if notes and "ia3" in str(wl["kw"].get("preset", "")) + wl["note"]:
             out["reference_notes"] = notes
         for lora in list(getattr(net, "loras", [])):
             lora.restore()
@@ -935,6 +937,9 @@ def run_reference_cpu(args):
 
 
 def main():
+    import logging
+
+    logging.getLogger("LyCORIS").setLevel(logging.ERROR)  # keep stdout to the ONE JSON line
     args = parse()
     if args.impl == "reference":
         run_reference_cpu(args)

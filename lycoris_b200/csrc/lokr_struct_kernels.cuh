@@ -57,9 +57,10 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8], int fmt) {
 
 // out[m, a, c] = sum_b Wm(a, b) * in[m, b, c]      in: [M, nb, nc]   out: [M, na, nc]   16-bit, nc % 8 == 0
 // Wm(a, b) = w[a * ldw + b]  (trans = 0)   or   w[b * ldw + a]  (trans = 1)
-// One thread owns one (m, 8-column vector): streams the nb input vectors once (16-byte loads) and keeps the NA
-// output vectors in registers.  8 + 8 bytes of HBM traffic per 2*na*nb/…  FMAs: bandwidth-bound.
-template <int NA>
+// One thread owns one (m, 8-column vector): issues the NB input loads (16 bytes each) back to back — NB * 16 bytes in
+// flight per thread, which is what keeps HBM busy at ~2 resident CTAs per SM — and keeps the NA output vectors in
+// registers.  2 bytes read + 2 bytes written per element against 2*na FMAs: bandwidth-bound.
+template <int NA, int NB>
 __global__ void __launch_bounds__(256) lokr_mix_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out,
                                                        const void* __restrict__ w, int w_dtype, int ldw, int trans,
                                                        int64_t M, int na, int nb, int nc8, int fmt) {
@@ -80,15 +81,22 @@ __global__ void __launch_bounds__(256) lokr_mix_kernel(const uint16_t* __restric
     for (int a = 0; a < NA; ++a)
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[a][j] = 0.f;
-    for (int b = 0; b < nb; ++b) {
-      float x[8];
-      unpack8(__ldg(src + static_cast<int64_t>(b) * nc8), x, fmt);
+    uint4 raw[NB];
 #pragma unroll
-      for (int a = 0; a < NA; ++a) {
-        if (a < na) {
-          const float wv = sw[a * nb + b];
+    for (int b = 0; b < NB; ++b)
+      raw[b] = b < nb ? __ldg(src + static_cast<int64_t>(b) * nc8) : make_uint4(0, 0, 0, 0);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[a][j] = fmaf(wv, x[j], acc[a][j]);
+    for (int b = 0; b < NB; ++b) {
+      if (b < nb) {
+        float x[8];
+        unpack8(raw[b], x, fmt);
+#pragma unroll
+        for (int a = 0; a < NA; ++a) {
+          if (a < na) {
+            const float wv = sw[a * nb + b];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[a][j] = fmaf(wv, x[j], acc[a][j]);
+          }
         }
       }
     }

@@ -822,10 +822,10 @@ int lyco_lokr_mix(const void* in, void* out, const void* w, int w_dtype, int ldw
   const int fmt = dtype == LYCO_BF16 ? 1 : 0;
   const uint16_t* src = static_cast<const uint16_t*>(in);
   uint16_t* dst = static_cast<uint16_t*>(out);
-  if (na <= 4)
-    lyco::lokr_mix_kernel<4><<<static_cast<int>(grid), 256, 0, stream>>>(src, dst, w, w_dtype, ldw, transpose, M, na, nb, nc8, fmt);
+  if (na <= 4 && nb <= 4)
+    lyco::lokr_mix_kernel<4, 4><<<static_cast<int>(grid), 256, 0, stream>>>(src, dst, w, w_dtype, ldw, transpose, M, na, nb, nc8, fmt);
   else
-    lyco::lokr_mix_kernel<8><<<static_cast<int>(grid), 256, 0, stream>>>(src, dst, w, w_dtype, ldw, transpose, M, na, nb, nc8, fmt);
+    lyco::lokr_mix_kernel<8, 8><<<static_cast<int>(grid), 256, 0, stream>>>(src, dst, w, w_dtype, ldw, transpose, M, na, nb, nc8, fmt);
   LYCO_CUDA(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
