@@ -176,7 +176,7 @@ def import_reference():
     except Exception as e:  # noqa: BLE001
         return None, f"import failed: {type(e).__name__}: {e}"
     notes = []
-    logging.getLogger("LyCORIS").setLevel(logging.ERROR)
+    logging.getLogger("LyCORIS").setLevel(logging.ERROR)  # the reference's logging module resets it to INFO at import
     if "ia3" not in ref_wrapper.network_module_dict:
         # upstream omission (lycoris/wrapper.py:45-55): the class exists but is not registered, so any preset that
         # names algo="ia3" raises KeyError.  Registering the reference's OWN class is the one change made.
@@ -937,7 +937,7 @@ def run_reference_cpu(args):
 
 
 def main():
-    import logging
+    import lycoris_b200.logging  # noqa: F401  (the package logger sets its level at import: import first, then quiet it)
 
     logging.getLogger("LyCORIS").setLevel(logging.ERROR)  # keep stdout to the ONE JSON line
     args = parse()
