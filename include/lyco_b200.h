@@ -237,19 +237,22 @@ int lyco_grad_prep(const float* dW, const void* P, void* G, int64_t n, float gsc
  * reference's structured Kronecker contraction, lycoris/modules/lokr.py:517-530 (F.linear over the group axis).
  * Then  g_w2 = lyco_gemm(dY as [M*up, vp]ᵀ, Xt as [M*up, vq])  — one contraction with 1/uq of the FLOPs of the
  * dense dW' = dYᵀ·X that autograd runs for `delta_weight` (lokr.py:565) — and g_w1 comes from lyco_lokr_w1grad.
+ * zero_buf / zero_n: optional fp32 array the kernel also zero-fills (the gradient buffers the following
+ * accumulate-mode lyco_gemm and lyco_lokr_w1grad reduce into), so no memset node sits between the kernels.
  */
 int lyco_lokr_mix(const void* in, void* out, const void* w, int w_dtype, int ldw, int transpose,
-                  int64_t M, int na, int nb, int nc, int dtype, void* stream);
+                  int64_t M, int na, int nb, int nc, int dtype, float* zero_buf, int64_t zero_n, void* stream);
 
 /*
  * g_w1[a, b] = gscale * sum_{m, c} P[m, a, c] * R[m, b, c];  P is [M, na, nc], R is [M, nb, nc] (16-bit, `dtype`),
- * g_w1 fp32 [na, nb], zero-filled by the call.  nc % 8 == 0, na, nb <= 8.
+ * g_w1 fp32 [na, nb], zero-filled by the call when zero_fill != 0 (else it must already be zero: the sums are
+ * added with atomics).  nc % 8 == 0, na, nb <= 8.
  * With Q = dY2·w2 ([M*up, vq], one lyco_gemm) and X [M, uq, vq]:  g_w1[pu,u] = sum_{m,v} Q[m,pu,v] X[m,u,v]
  * (or P = dY, R = H = X2·w2ᵀ when dY is the mixed side).  Replaces torch.kron's backward reduction over the dense
  * d(delta_weight) for lokr_w1 (lycoris/functional/lokr.py:11-20 under autograd).
  */
 int lyco_lokr_w1grad(const void* P, const void* R, float* g_w1, int64_t M, int na, int nb, int nc,
-                     float gscale, int dtype, void* stream);
+                     float gscale, int dtype, int zero_fill, void* stream);
 
 /* ------------------------------------------------------------------------- */
 /* delta weight / DoRA (merge_to, onfly_merge, apply_max_norm, dora_wd)       */

@@ -63,8 +63,14 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8], int fmt) {
 template <int NA, int NB>
 __global__ void __launch_bounds__(256) lokr_mix_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out,
                                                        const void* __restrict__ w, int w_dtype, int ldw, int trans,
-                                                       int64_t M, int na, int nb, int nc8, int fmt) {
+                                                       int64_t M, int na, int nb, int nc8, int fmt,
+                                                       float* __restrict__ zero_buf, int64_t zero_n) {
   __shared__ float sw[LK_MAX_G * LK_MAX_G];
+  // optional side job: zero-fill the (small) fp32 gradient buffers the NEXT kernels reduce into with atomics — this
+  // kernel precedes them on the stream, so the two memset nodes per layer-step disappear from the captured graph
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < zero_n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    zero_buf[i] = 0.f;
   for (int i = threadIdx.x; i < na * nb; i += blockDim.x) {
     const int a = i / nb, b = i % nb;
     sw[i] = ld_f(w, w_dtype, trans ? static_cast<int64_t>(b) * ldw + a : static_cast<int64_t>(a) * ldw + b);

@@ -804,7 +804,7 @@ int lyco_grad_prep(const float* dW, const void* P, void* G, int64_t n, float gsc
 }
 
 int lyco_lokr_mix(const void* in, void* out, const void* w, int w_dtype, int ldw, int transpose, int64_t M, int na,
-                  int nb, int nc, int dtype, void* stream_) {
+                  int nb, int nc, int dtype, float* zero_buf, int64_t zero_n, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!in || !out || !w) return fail("lyco_lokr_mix: null operand");
   if (dtype != LYCO_BF16 && dtype != LYCO_F16) return fail("lyco_lokr_mix: activations must be bf16/f16");
@@ -812,6 +812,7 @@ int lyco_lokr_mix(const void* in, void* out, const void* w, int w_dtype, int ldw
     return fail("lyco_lokr_mix: needs M > 0, 1 <= na, nb <= 8, nc %% 8 == 0 (M=%lld na=%d nb=%d nc=%d)", (long long)M, na, nb, nc);
   if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15)
     return fail("lyco_lokr_mix: arrays must be 16-byte aligned");
+  if (zero_n < 0 || (zero_n > 0 && !zero_buf)) return fail("lyco_lokr_mix: bad zero-fill request");
   DeviceInfo di;
   if (device_info(&di)) return 1;
   const int nc8 = nc / 8;
@@ -823,16 +824,16 @@ int lyco_lokr_mix(const void* in, void* out, const void* w, int w_dtype, int ldw
   const uint16_t* src = static_cast<const uint16_t*>(in);
   uint16_t* dst = static_cast<uint16_t*>(out);
   if (na <= 4 && nb <= 4)
-    lyco::lokr_mix_kernel<4, 4><<<static_cast<int>(grid), 256, 0, stream>>>(src, dst, w, w_dtype, ldw, transpose, M, na, nb, nc8, fmt);
+    lyco::lokr_mix_kernel<4, 4><<<static_cast<int>(grid), 256, 0, stream>>>(src, dst, w, w_dtype, ldw, transpose, M, na, nb, nc8, fmt, zero_buf, zero_n);
   else
-    lyco::lokr_mix_kernel<8, 8><<<static_cast<int>(grid), 256, 0, stream>>>(src, dst, w, w_dtype, ldw, transpose, M, na, nb, nc8, fmt);
+    lyco::lokr_mix_kernel<8, 8><<<static_cast<int>(grid), 256, 0, stream>>>(src, dst, w, w_dtype, ldw, transpose, M, na, nb, nc8, fmt, zero_buf, zero_n);
   LYCO_CUDA(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }
 
 int lyco_lokr_w1grad(const void* P, const void* R, float* g_w1, int64_t M, int na, int nb, int nc, float gscale,
-                     int dtype, void* stream_) {
+                     int dtype, int zero_fill, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!P || !R || !g_w1) return fail("lyco_lokr_w1grad: null operand");
   if (dtype != LYCO_BF16 && dtype != LYCO_F16) return fail("lyco_lokr_w1grad: activations must be bf16/f16");
@@ -842,7 +843,7 @@ int lyco_lokr_w1grad(const void* P, const void* R, float* g_w1, int64_t M, int n
     return fail("lyco_lokr_w1grad: arrays must be 16-byte aligned");
   DeviceInfo di;
   if (device_info(&di)) return 1;
-  LYCO_CUDA(cudaMemsetAsync(g_w1, 0, sizeof(float) * static_cast<size_t>(na) * nb, stream));
+  if (zero_fill) LYCO_CUDA(cudaMemsetAsync(g_w1, 0, sizeof(float) * static_cast<size_t>(na) * nb, stream));
   const int nc8 = nc / 8;
   const int64_t work = M * nc8;
   int64_t grid = (work + 255) / 256;

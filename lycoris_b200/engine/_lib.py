@@ -121,11 +121,11 @@ def _bind(lib):
     lib.lyco_lokr_mix.restype = c_int
     lib.lyco_lokr_mix.argtypes = [
         c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,  # in out w w_dtype ldw transpose
-        c_int64, c_int, c_int, c_int, c_int, c_void_p,  # M na nb nc dtype stream
+        c_int64, c_int, c_int, c_int, c_int, c_void_p, c_int64, c_void_p,  # M na nb nc dtype zero_buf zero_n stream
     ]
     lib.lyco_lokr_w1grad.restype = c_int
     lib.lyco_lokr_w1grad.argtypes = [
-        c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_float, c_int, c_void_p,
+        c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_float, c_int, c_int, c_void_p,
     ]
     lib.lyco_delta_weight.restype = c_int
     lib.lyco_delta_weight.argtypes = [POINTER(DeltaDesc), c_void_p, c_void_p, c_int, c_void_p, c_void_p]

@@ -281,27 +281,32 @@ def grad_prep(dW: torch.Tensor, P, gscale: float, dtype: torch.dtype) -> torch.T
     return G
 
 
-def lokr_mix(x, w1, na, nb, nc, transpose):
+def lokr_mix(x, w1, na, nb, nc, transpose, zero=None):
     """``out[m, a, c] = sum_b Wm(a, b) * x[m, b, c]`` with ``Wm = w1`` (or ``w1ᵀ``); ``x`` is a contiguous 16-bit
-    ``[M, nb*nc]`` array, the result ``[M, na*nc]`` (lyco_lokr_mix)."""
-    _require_cuda(x, w1)
+    ``[M, nb*nc]`` array, the result ``[M, na*nc]`` (lyco_lokr_mix).  ``zero``: optional contiguous fp32 tensor the
+    kernel zero-fills on the side (gradient buffers of the kernels that follow)."""
+    _require_cuda(x, w1, zero)
     M = x.shape[0]
     assert x.is_contiguous() and x.shape[1] == nb * nc and w1.is_contiguous()
+    assert zero is None or (zero.dtype == torch.float32 and zero.is_contiguous())
     out = torch.empty((M, na * nc), device=x.device, dtype=x.dtype)
     rc = _lib.load().lyco_lokr_mix(_ptr(x), _ptr(out), _ptr(w1), dtype_code(w1.dtype), w1.stride(0), int(transpose),
-                                   M, na, nb, nc, dtype_code(x.dtype), _stream())
+                                   M, na, nb, nc, dtype_code(x.dtype), _ptr(zero), 0 if zero is None else zero.numel(),
+                                   _stream())
     _lib.check(rc, "lokr_mix")
     return out
 
 
-def lokr_w1grad(P, R, na, nb, nc, gscale):
-    """fp32 ``g[a, b] = gscale * sum_{m,c} P[m, a, c] * R[m, b, c]`` (lyco_lokr_w1grad)."""
-    _require_cuda(P, R)
+def lokr_w1grad(P, R, na, nb, nc, gscale, out=None):
+    """fp32 ``g[a, b] = gscale * sum_{m,c} P[m, a, c] * R[m, b, c]`` (lyco_lokr_w1grad).  ``out``: an fp32 ``[na, nb]``
+    buffer that is ALREADY zero (e.g. zero-filled by lokr_mix) — the sums are added to it without a memset."""
+    _require_cuda(P, R, out)
     M = P.shape[0]
     assert P.is_contiguous() and R.is_contiguous() and P.shape[1] == na * nc and R.shape[1] == nb * nc and R.shape[0] == M
-    g = torch.empty((na, nb), device=P.device, dtype=torch.float32)
+    g = out if out is not None else torch.empty((na, nb), device=P.device, dtype=torch.float32)
+    assert g.dtype == torch.float32 and g.is_contiguous() and g.numel() == na * nb
     rc = _lib.load().lyco_lokr_w1grad(_ptr(P), _ptr(R), _ptr(g), M, na, nb, nc, float(gscale), dtype_code(P.dtype),
-                                      _stream())
+                                      int(out is None), _stream())
     _lib.check(rc, "lokr_w1grad")
     return g
 

@@ -299,20 +299,26 @@ def _lokr_structured_grads(spec, factors, dy2, x2):
     gscale = spec.m_pre * spec.m_post1 * spec.m_post2
     w2c = w2 if w2.dtype == cdt else w2.to(cdt)
     f32 = torch.float32
+    # one fp32 buffer for both gradients, zero-filled by the mix kernel on the side (no memset nodes in the graph):
+    # g_w1 (up*uq floats, padded to 64) followed by g_w2 — the skinny GEMM and the w1 reduction ADD into it
+    n1 = (up * uq + 63) // 64 * 64
+    flat = torch.empty(n1 + vp * vq, device=x2.device, dtype=f32)
+    g_w1 = flat[: up * uq].view(up, uq)
+    g_w2 = flat[n1:].view(vp, vq)
     if up * vq <= uq * vp:
         # mix the (smaller) input side:  Xt[m,pu,v] = sum_u w1[pu,u] X[m,u,v]
-        Xt = K.lokr_mix(x2, w1, up, uq, vq, transpose=False)
+        Xt = K.lokr_mix(x2, w1, up, uq, vq, transpose=False, zero=flat)
         dY2 = dy2.view(M * up, vp)
-        g_w2 = K.gemm(dY2, Xt.view(M * up, vq), a_mn=True, b_mn=True, out_dtype=f32)     # [vp, vq]
+        K.gemm(dY2, Xt.view(M * up, vq), a_mn=True, b_mn=True, out=g_w2, out_dtype=f32, accumulate=True)   # [vp, vq]
         Q = K.gemm(dY2, w2c.t().contiguous())                                            # dY2 · w2   [M*up, vq]
-        g_w1 = K.lokr_w1grad(Q.view(M, up * vq), x2, up, uq, vq, gscale)
+        K.lokr_w1grad(Q.view(M, up * vq), x2, up, uq, vq, gscale, out=g_w1)
     else:
         # mix the output-gradient side:  Z[m,u,pv] = sum_pu w1[pu,u] dY[m,pu,pv]
-        Z = K.lokr_mix(dy2, w1, uq, up, vp, transpose=True)
+        Z = K.lokr_mix(dy2, w1, uq, up, vp, transpose=True, zero=flat)
         X2 = x2.view(M * uq, vq)
-        g_w2 = K.gemm(Z.view(M * uq, vp), X2, a_mn=True, b_mn=True, out_dtype=f32)       # [vp, vq]
+        K.gemm(Z.view(M * uq, vp), X2, a_mn=True, b_mn=True, out=g_w2, out_dtype=f32, accumulate=True)      # [vp, vq]
         H = K.gemm(X2, w2c.contiguous())                                                 # X2 · w2ᵀ   [M*uq, vp]
-        g_w1 = K.lokr_w1grad(dy2, H.view(M, uq * vp), up, uq, vp, gscale)
+        K.lokr_w1grad(dy2, H.view(M, uq * vp), up, uq, vp, gscale, out=g_w1)
     if gscale != 1.0:
         g_w2 = g_w2 * gscale
     return [g_w1, g_w2]

@@ -24,7 +24,9 @@ def test_lokr_mix_kernel(na, nb, nc, transpose):
     M = 1000
     x = torch.randn(M, nb * nc, generator=g).cuda().to(torch.bfloat16)
     w = torch.randn((nb, na) if transpose else (na, nb), generator=g).cuda()
-    out = K.lokr_mix(x, w, na, nb, nc, transpose)
+    side = torch.full((777,), 3.0, device="cuda")  # zero-filled on the side by the same launch
+    out = K.lokr_mix(x, w, na, nb, nc, transpose, zero=side)
+    assert float(side.abs().sum()) == 0.0
     wm = w.t() if transpose else w
     ref = torch.einsum("ab,mbc->mac", wm.float(), x.float().view(M, nb, nc)).reshape(M, na * nc)
     assert out.shape == (M, na * nc) and out.dtype == torch.bfloat16
@@ -42,6 +44,8 @@ def test_lokr_w1grad_kernel(na, nb, nc):
     out = K.lokr_w1grad(P, R, na, nb, nc, 0.5)
     ref = 0.5 * torch.einsum("mac,mbc->ab", P.double().view(M, na, nc), R.double().view(M, nb, nc))
     assert rel_err(out, ref.float()) <= 1e-4
+    pre = torch.zeros(na, nb, device="cuda")  # caller-zeroed buffer: added to, no memset inside
+    assert K.lokr_w1grad(P, R, na, nb, nc, 0.5, out=pre) is pre and rel_err(pre, ref.float()) <= 1e-4
 
 
 SHAPES = [
