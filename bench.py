@@ -621,7 +621,10 @@ def profile_one_step(args, step):
             a[1] += k.duration
     if args.kernel_table:
         with open(args.kernel_table + ".attribution", "w") as fh:
-            for title, d in (("launched inside the engine's autograd nodes", inside), ("model side (outside)", outside)):
+            # kernels launched through the C-ABI have no ATen parent op, so they land in the second group with the model
+            for title, d in (("ATen / library kernels launched INSIDE the engine's autograd nodes (what is left of PyTorch "
+                              "on the adapter path)", inside),
+                             ("everything else: the engine's own kernels (C-ABI launches) + the model's ops", outside)):
                 tot_d = sum(v[1] for v in d.values())
                 fh.write(f"{title}: {tot_d / 1e3:.2f} ms\n")
                 for name, (cnt, t) in sorted(d.items(), key=lambda kv: -kv[1][1])[:14]:
