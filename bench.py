@@ -441,11 +441,24 @@ def run_engine(args):
     torch.cuda.synchronize()
     per_step_launches = _lib.launch_count() - l0
     K.set_gemm_profiler(None)
-    gemm_ms = sum(e0.elapsed_time(e1) for e0, e1, *_ in sink)
-    gemm_flops = sum(f for _, _, f, *_ in sink)
+    # split the launches by arithmetic intensity: contractions above the ridge (peak FLOP/s / peak B/s) are bound by the
+    # tensor pipe — the dominant kernel class, `roofline` — the skinny structured-gradient contractions below it are
+    # HBM-bound and are reported against the copy bandwidth instead (`roofline_hbm_gemm`)
+    try:
+        _pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        _pk = {}
+    ridge = _pk.get("bf16_tflops_sustained", 1400.0) * 1e12 / (_pk.get("hbm_gbs", 6650.0) * 1e9)
+    dense = [r for r in sink if r[2] / r[6] >= ridge]
+    skinny = [r for r in sink if r[2] / r[6] < ridge]
+    gemm_ms = sum(r[0].elapsed_time(r[1]) for r in dense)
+    gemm_flops = sum(r[2] for r in dense)
+    skinny_ms = sum(r[0].elapsed_time(r[1]) for r in skinny)
+    skinny_bytes = sum(r[6] for r in skinny)
+    skinny_flops = sum(r[2] for r in skinny)
     if args.kernel_table and rank == 0:
         by_shape = {}
-        for e0_, e1_, fl, M_, N_, K_ in sink:
+        for e0_, e1_, fl, M_, N_, K_, _b in sink:
             a = by_shape.setdefault((M_, N_, K_), [0, 0.0, 0.0])
             a[0] += 1
             a[1] += e0_.elapsed_time(e1_)
@@ -529,14 +542,16 @@ def run_engine(args):
             # dram__bytes_read+write per launch of the dominant GEMM from a committed `ncu --set full` capture
             "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
             "traffic_source": traffic,
-            "gemm_launches_per_step": len(sink), "gemm_ms_per_step": gemm_ms, "gemm_share_of_eager_step": gemm_ms / eager_ms,
+            "gemm_launches_per_step": len(dense), "gemm_ms_per_step": gemm_ms, "gemm_share_of_eager_step": gemm_ms / eager_ms,
+            "ridge_flop_per_byte": ridge,
             "eager_step_ms_gpu_bound": eager_ms,
             # FLOPs the GEMM launches EXECUTE (every contraction the engine runs, structured or dense)
             "executed_tflop_per_step": gemm_flops / 1e12,
             # the event brackets above also contain the split-K memsets and the stream front-end gap per launch;
             # the same launches by CUPTI kernel duration (torch.profiler over one eager step):
             "gemm_kernel_ms_per_step_cupti": gemm_kernel_ms,
-            "achieved_cupti": (gemm_flops / (gemm_kernel_ms * 1e-3) / 1e12) if gemm_kernel_ms else None,
+            # (CUPTI totals cannot be split by shape: ALL gemm_sm100_kernel launches, tensor-bound and HBM-bound alike)
+            "achieved_cupti_all_gemm_launches": ((gemm_flops + skinny_flops) / (gemm_kernel_ms * 1e-3) / 1e12) if gemm_kernel_ms else None,
             # ALGORITHMIC work of the adapter path (c*F1 + F_side, c = 2 or 3 — never the
             # reference's redundant 5*F1) over the WHOLE step time, model-side ops included
             "algorithmic": {
@@ -548,6 +563,17 @@ def run_engine(args):
         },
         "clocks": clocks.summary(),
     }
+    if skinny:
+        hbm = peaks.get("hbm_gbs", 6650.0)
+        result["roofline_hbm_gemm"] = {
+            "bound": "hbm", "kernel": "gemm_sm100_kernel launches below the ridge (structured LoKr g_w2 / Q contractions, rank-r "
+                                      "products, M = 8 time-embedding layers)",
+            "achieved": skinny_bytes / (skinny_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+            "frac": skinny_bytes / (skinny_ms * 1e-3) / 1e9 / hbm,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+            "launches_per_step": len(skinny), "ms_per_step": skinny_ms, "algorithmic_bytes_per_step": skinny_bytes,
+            "executed_tflop_per_step": skinny_flops / 1e12,
+        }
     if dp is not None:
         result["allreduce_exposed_ms"] = allreduce_exposed_ms
         result["allreduce"] = {"buckets_issued_inside_backward": buckets_overlapped[0], "buckets": buckets_overlapped[1],

@@ -49,7 +49,7 @@ def gemm_supported(*mats) -> bool:
     return True
 
 
-_gemm_profile = None  # bench.py: list collecting (start_event, end_event, flops, M, N, K) per launch
+_gemm_profile = None  # bench.py: list collecting (start_event, end_event, flops, M, N, K, bytes) per launch
 
 
 def set_gemm_profiler(sink):
@@ -96,7 +96,8 @@ def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, out_dtype=None, split_k=0, 
     _lib.check(rc, "gemm")
     if prof is not None:
         e1.record()
-        prof.append((e0, e1, 2.0 * M * N * K, M, N, K))
+        prof.append((e0, e1, 2.0 * M * N * K, M, N, K,
+                     float(a.element_size() * (M * K + N * K) + out.element_size() * M * N)))  # + algorithmic bytes
     return out
 
 
