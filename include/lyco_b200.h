@@ -93,6 +93,23 @@ int lyco_gemm(const void* A, int a_mn_major, int64_t lda,
               int M, int N, int K,
               int ab_dtype, int split_k, int accumulate, void* stream);
 
+/*
+ * C[M,N] = A·Bᵀ + A2·B2ᵀ (+ bias): two operand pairs accumulated into ONE TMEM accumulator by the same kernel —
+ * the skinny rank-r side path of a low-rank adapter next to the dense base contraction, with no merged weight.
+ *   A  [M, K]  row-major (K-major),   B  [N, K] (b_mn_major = 0) or [K, N] (b_mn_major = 1)
+ *   A2 [M, K2] row-major,             B2 [N, K2] or [K2, N] with the SAME major-ness as B
+ *   C 16-bit, same dtype as the operands; K2 is padded to the 64-element k-block by TMA zero fill.
+ * LoCon / DyLoRA on nn.Linear:
+ *   forward   T = X·downᵀ [M,r] (lyco_gemm),   Y  = X·Wᵀ + T·(s·up)ᵀ + b        (A2 = T,  B2 = s·up [N, r])
+ *   backward  U = dY·(s·up) [M,r] (lyco_gemm), dX = dY·W + U·down                (A2 = U,  B2 = down [r, K], MN-major)
+ *             g_up = s·dYᵀ·T,  g_down = Uᵀ·X   (skinny lyco_gemm calls) — no dW' = dYᵀ·X, no W' = W + dW pass.
+ * Replaces `org_forward(x)` + `make_weight` + `W + dW` + `self.op(x, delta_weight)` + add (lycoris/modules/locon.py:
+ * 309-332) in the contraction ORDER of the reference's own bypass path (locon.py:273-307: lora_down, then lora_up).
+ */
+int lyco_gemm_dual(const void* A, int64_t lda, const void* B, int b_mn_major, int64_t ldb, int K,
+                   const void* A2, int64_t lda2, const void* B2, int64_t ldb2, int K2,
+                   void* C, int64_t ldc, const void* bias, int bias_dtype, int M, int N, int dtype, void* stream);
+
 /* ------------------------------------------------------------------------- */
 /* implicit-GEMM convolution (tcgen05 + TMA im2col)                           */
 /* ------------------------------------------------------------------------- */
@@ -276,11 +293,14 @@ int lyco_delta_weight(const lyco_delta_desc_t* d, const void* W, void* dW_out, i
  *   sumsq[g] = sum over group g of Wm^2      groups: output rows (on_out = 1) or input channels (K'/taps of them)
  *   s[g]     = dora_scale[g] / (sqrt(sumsq[g]) + eps);   s <- mult*(s - 1) + 1 when mult != 1
  *   W_out    = rnd_w(Wm * s[group])
+ * scale_dtype: the dtype the reference evaluates the norm / quotient / product in (dora_scale's dtype: LYCO_F32
+ * under autocast; LYCO_BF16 / LYCO_F16 for a 16-bit adapter, whose roundings of the norm and of the scale are then
+ * reproduced); eps is that dtype's machine epsilon, passed by the caller.
  * sumsq (fp32 [groups]) is zero-filled and written by the call and kept by the caller for the backward.
  * Replaces apply_weight_decompose, lycoris/modules/locon.py:239-260 (copies in loha.py / lokr.py).
  */
 int lyco_dora_fwd(const void* Wm, void* W_out, const float* dora_scale, float* sumsq, int N, int K, int on_out,
-                  int taps, float mult, float eps, int w_dtype, void* stream);
+                  int taps, float mult, float eps, int w_dtype, int scale_dtype, void* stream);
 
 /*
  * Backward of lyco_dora_fwd, in place: dW (fp32 [N,K'], = dYᵀ·X of the contraction with W_out) becomes dWm, and
@@ -291,7 +311,7 @@ int lyco_dora_fwd(const void* Wm, void* W_out, const float* dora_scale, float* s
  */
 int lyco_dora_bwd(float* dW, const void* Wm, const float* dora_scale, const float* sumsq, float* t,
                   float* g_scale, int N, int K, int on_out, int taps, float mult, float eps, int w_dtype,
-                  void* stream);
+                  int scale_dtype, void* stream);
 
 #ifdef __cplusplus
 }

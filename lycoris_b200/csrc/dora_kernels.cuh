@@ -51,10 +51,13 @@ __global__ void __launch_bounds__(256) dora_reduce_kernel(const void* __restrict
   }
 }
 
-// scale of a group from its squared norm: s = g / (sqrt(sumsq) + eps), then s <- mult * (s - 1) + 1 when mult != 1
-__device__ __forceinline__ float dora_scale_of(float sumsq, float g, float mult, float eps) {
-  float s = g / (sqrtf(sumsq) + eps);
-  if (mult != 1.f) s = mult * (s - 1.f) + 1.f;
+// scale of a group from its squared norm: s = g / (sqrt(sumsq) + eps), then s <- mult * (s - 1) + 1 when mult != 1.
+// `sdt` is the dtype the reference does this arithmetic in (dora_scale's: fp32 under autocast; a bf16 adapter rounds the
+// norm, the sum with eps and the quotient to bf16 — a per-group relative difference of up to 2^-8 if ignored).
+__device__ __forceinline__ float dora_scale_of(float sumsq, float g, float mult, float eps, int sdt) {
+  const float n = rnd(sqrtf(sumsq), sdt);
+  float s = rnd(g / rnd(n + eps, sdt), sdt);
+  if (mult != 1.f) s = rnd(rnd(mult * rnd(s - 1.f, sdt), sdt) + 1.f, sdt);
   return s;
 }
 
@@ -62,14 +65,14 @@ __device__ __forceinline__ float dora_scale_of(float sumsq, float g, float mult,
 __global__ void __launch_bounds__(256) dora_apply_fwd_kernel(const uint16_t* __restrict__ Wm, uint16_t* __restrict__ Wout,
                                                              const float* __restrict__ sumsq, const float* __restrict__ g,
                                                              int N, int K, int on_out, int taps, float mult, float eps,
-                                                             int w_dtype) {
+                                                             int w_dtype, int sdt) {
   const int64_t total = static_cast<int64_t>(N) * K;
   for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
        idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int n = static_cast<int>(idx / K), k = static_cast<int>(idx % K);
     const int grp = dora_group(n, k, on_out, taps);
-    const float s = dora_scale_of(__ldg(sumsq + grp), __ldg(g + grp), mult, eps);
-    Wout[idx] = to16(cvt16(Wm[idx], w_dtype) * s, w_dtype);
+    const float s = dora_scale_of(__ldg(sumsq + grp), __ldg(g + grp), mult, eps, sdt);
+    Wout[idx] = to16(rnd(cvt16(Wm[idx], w_dtype) * s, sdt), w_dtype);
   }
 }
 
@@ -80,7 +83,7 @@ __global__ void __launch_bounds__(256) dora_apply_bwd_kernel(float* __restrict__
                                                              const float* __restrict__ sumsq, const float* __restrict__ g,
                                                              const float* __restrict__ t, float* __restrict__ dg, int N,
                                                              int K, int on_out, int taps, float mult, float eps,
-                                                             int w_dtype, int groups) {
+                                                             int w_dtype, int groups, int sdt) {
   const int64_t total = static_cast<int64_t>(N) * K;
   const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (dg != nullptr && tid < groups) {
@@ -92,7 +95,7 @@ __global__ void __launch_bounds__(256) dora_apply_bwd_kernel(float* __restrict__
     const int grp = dora_group(n_, k, on_out, taps);
     const float ss = __ldg(sumsq + grp), gg = __ldg(g + grp), tt = __ldg(t + grp);
     const float nrm = sqrtf(ss), ne = nrm + eps;
-    const float s = dora_scale_of(ss, gg, mult, eps);
+    const float s = dora_scale_of(ss, gg, mult, eps, sdt);
     const float b = nrm > 0.f ? mult * gg * tt / (ne * ne * nrm) : 0.f;
     dW[idx] = s * dW[idx] - b * cvt16(Wm[idx], w_dtype);
   }

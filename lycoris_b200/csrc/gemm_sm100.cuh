@@ -53,6 +53,8 @@ struct GemmParams {
   int64_t ldc;
   int M, N, K;
   int m_tiles, n_tiles, splits, k_blocks;
+  int k_blocks1;    // k-blocks [0, k_blocks1) read operand pair (A, B); [k_blocks1, k_blocks) read the SECOND pair
+                    // (A2, B2) into the same accumulator: C = A·Bᵀ + A2·B2ᵀ (the rank-r side path of a low-rank adapter)
   int block_n;      // columns per tile (multiple of 32; MN-major B: of 64, pairs: of 128)
   int stages;       // smem ring depth for this block_n
   int fmt;          // operand / 16-bit output format: 0 = f16, 1 = bf16
@@ -331,7 +333,8 @@ __device__ __forceinline__ void gemm_epilogue_tile(uint32_t t_row, int row0, int
 template <bool PAIR, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                  const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
+                  const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_a2,
+                  const __grid_constant__ CUtensorMap tmap_b2, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -355,6 +358,10 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     ptx::prefetch_tmap(&tmap_a);
     ptx::prefetch_tmap(&tmap_b);
     if (epi_uses_tma(EPI)) ptx::prefetch_tmap(&tmap_c);
+    if (p.k_blocks1 < p.k_blocks) {
+      ptx::prefetch_tmap(&tmap_a2);
+      ptx::prefetch_tmap(&tmap_b2);
+    }
   }
   gemm_setup<PAIR>(full_bar, empty_bar, tfull_bar, tempty_bar, tmem_slot, stages, warp, lane);
   const uint32_t tmem_base = *tmem_slot;
@@ -376,36 +383,41 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * stage_bytes;
         uint8_t* sb = sa + GEMM_A_BYTES;
+        // second operand pair (side path): same tile coordinates, its own reduction index
+        const bool second = kb >= p.k_blocks1;
+        const CUtensorMap* ma = second ? &tmap_a2 : &tmap_a;
+        const CUtensorMap* mb = second ? &tmap_b2 : &tmap_b;
+        const int kc = (second ? kb - p.k_blocks1 : kb) * GEMM_BLOCK_K;
         if (PAIR) {
           const uint32_t full_leader = ptx::mapa(ptx::smem_u32(&full_bar[stage]), 0);
           ptx::mbar_expect_tx_cluster(full_leader, stage_bytes);
           if (!A_MN) {
-            ptx::tma_load_2d_pair(sa, &tmap_a, full_leader, kb * GEMM_BLOCK_K, m0);
+            ptx::tma_load_2d_pair(sa, ma, full_leader, kc, m0);
           } else {
 #pragma unroll
             for (int j = 0; j < GEMM_BLOCK_M / 64; ++j)
-              ptx::tma_load_2d_pair(sa + j * GEMM_ATOM_BYTES, &tmap_a, full_leader, m0 + j * 64, kb * GEMM_BLOCK_K);
+              ptx::tma_load_2d_pair(sa + j * GEMM_ATOM_BYTES, ma, full_leader, m0 + j * 64, kc);
           }
           if (!B_MN) {
-            ptx::tma_load_2d_pair(sb, &tmap_b, full_leader, kb * GEMM_BLOCK_K, n0);
+            ptx::tma_load_2d_pair(sb, mb, full_leader, kc, n0);
           } else {
             for (int j = 0; j < b_rows / 64; ++j)
-              ptx::tma_load_2d_pair(sb + j * GEMM_ATOM_BYTES, &tmap_b, full_leader, n0 + j * 64, kb * GEMM_BLOCK_K);
+              ptx::tma_load_2d_pair(sb + j * GEMM_ATOM_BYTES, mb, full_leader, n0 + j * 64, kc);
           }
         } else {
           ptx::mbar_expect_tx(&full_bar[stage], stage_bytes);
           if (!A_MN) {
-            ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * GEMM_BLOCK_K, m0);
+            ptx::tma_load_2d(sa, ma, &full_bar[stage], kc, m0);
           } else {
 #pragma unroll
             for (int j = 0; j < GEMM_BLOCK_M / 64; ++j)
-              ptx::tma_load_2d(sa + j * GEMM_ATOM_BYTES, &tmap_a, &full_bar[stage], m0 + j * 64, kb * GEMM_BLOCK_K);
+              ptx::tma_load_2d(sa + j * GEMM_ATOM_BYTES, ma, &full_bar[stage], m0 + j * 64, kc);
           }
           if (!B_MN) {
-            ptx::tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * GEMM_BLOCK_K, n0);
+            ptx::tma_load_2d(sb, mb, &full_bar[stage], kc, n0);
           } else {
             for (int j = 0; j < b_rows / 64; ++j)
-              ptx::tma_load_2d(sb + j * GEMM_ATOM_BYTES, &tmap_b, &full_bar[stage], n0 + j * 64, kb * GEMM_BLOCK_K);
+              ptx::tma_load_2d(sb + j * GEMM_ATOM_BYTES, mb, &full_bar[stage], n0 + j * 64, kc);
           }
         }
         if (++stage == stages) { stage = 0; phase ^= 1; }

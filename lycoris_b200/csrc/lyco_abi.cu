@@ -201,24 +201,44 @@ int ensure_smem(Kern kern, bool* configured) {
   return 0;
 }
 
+// second operand pair of the dual-operand GEMM (C = A·Bᵀ + A2·B2ᵀ); plain GEMMs pass the first pair again (unused)
+struct SidePair {
+  const CUtensorMap* ta2;
+  const CUtensorMap* tb2;
+};
+
 template <bool PAIR, bool A_MN, bool B_MN, int EPI>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const lyco::GemmParams& p,
-                int grid, cudaStream_t stream) {
+                int grid, cudaStream_t stream, SidePair side) {
   auto kern = lyco::gemm_sm100_kernel<PAIR, A_MN, B_MN, EPI>;
   static bool configured[64] = {};
   if (ensure_smem(kern, configured)) return 1;
-  return launch_persistent(kern, PAIR, ta, tb, tc, p, grid, stream);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(lyco::GEMM_THREADS);
+  cfg.dynamicSmemBytes = lyco::GEMM_SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  LYCO_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, side.ta2 ? *side.ta2 : ta, side.tb2 ? *side.tb2 : tb, p));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
 }
 
 template <bool PAIR>
 int dispatch_gemm(bool a_mn, bool b_mn, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
-                  const lyco::GemmParams& p, int grid, cudaStream_t s) {
+                  const lyco::GemmParams& p, int grid, cudaStream_t s, SidePair side = SidePair{nullptr, nullptr}) {
   using namespace lyco;
-#define LYCO_EPI(AM, BM)                                                                             \
-  do {                                                                                               \
-    if (epi == EPI_STORE16) return launch_gemm<PAIR, AM, BM, EPI_STORE16>(ta, tb, tc, p, grid, s);   \
-    if (epi == EPI_STORE_F32) return launch_gemm<PAIR, AM, BM, EPI_STORE_F32>(ta, tb, tc, p, grid, s); \
-    return launch_gemm<PAIR, AM, BM, EPI_ATOMIC_F32>(ta, tb, tc, p, grid, s);                        \
+#define LYCO_EPI(AM, BM)                                                                                   \
+  do {                                                                                                     \
+    if (epi == EPI_STORE16) return launch_gemm<PAIR, AM, BM, EPI_STORE16>(ta, tb, tc, p, grid, s, side);   \
+    if (epi == EPI_STORE_F32) return launch_gemm<PAIR, AM, BM, EPI_STORE_F32>(ta, tb, tc, p, grid, s, side); \
+    return launch_gemm<PAIR, AM, BM, EPI_ATOMIC_F32>(ta, tb, tc, p, grid, s, side);                        \
   } while (0)
   if (!a_mn && !b_mn) LYCO_EPI(false, false);
   if (!a_mn && b_mn) LYCO_EPI(false, true);
@@ -434,7 +454,7 @@ int lyco_gemm(const void* A, int a_mn_major, int64_t lda, const void* B, int b_m
 
   lyco::GemmParams p;
   p.C = C; p.bias = bias; p.ldc = ldc; p.M = M; p.N = N; p.K = K;
-  p.m_tiles = m_tiles; p.n_tiles = n_tiles; p.splits = splits; p.k_blocks = k_blocks;
+  p.m_tiles = m_tiles; p.n_tiles = n_tiles; p.splits = splits; p.k_blocks = k_blocks; p.k_blocks1 = k_blocks;
   p.block_n = bn; p.stages = stages_for(tc.pair, bn);
   p.fmt = (ab_dtype == LYCO_BF16) ? 1 : 0;
   p.bias_dtype = bias_dtype;
@@ -453,6 +473,50 @@ int lyco_gemm(const void* A, int a_mn_major, int64_t lda, const void* B, int b_m
   const int workers = static_cast<int>(total < slots ? total : slots);
   if (tc.pair) return dispatch_gemm<true>(a_mn, b_mn, epi, ta, tb, tcm, p, 2 * workers, stream);
   return dispatch_gemm<false>(a_mn, b_mn, epi, ta, tb, tcm, p, workers, stream);
+}
+
+int lyco_gemm_dual(const void* A, int64_t lda, const void* B, int b_mn_major, int64_t ldb, int K, const void* A2,
+                   int64_t lda2, const void* B2, int64_t ldb2, int K2, void* C, int64_t ldc, const void* bias,
+                   int bias_dtype, int M, int N, int dtype, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (M <= 0 || N <= 0 || K <= 0 || K2 <= 0) return fail("lyco_gemm_dual: empty problem %d x %d x (%d + %d)", M, N, K, K2);
+  if (!A || !B || !A2 || !B2 || !C) return fail("lyco_gemm_dual: null operand");
+  if (dtype != LYCO_BF16 && dtype != LYCO_F16) return fail("lyco_gemm_dual: operands must be bf16/f16");
+  if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(A2) |
+       reinterpret_cast<uintptr_t>(B2) | reinterpret_cast<uintptr_t>(C)) & 15)
+    return fail("lyco_gemm_dual: operand base pointers must be 16-byte aligned");
+  if ((lda | ldb | lda2 | ldb2 | ldc) & 7) return fail("lyco_gemm_dual: leading dimensions must be multiples of 8");
+  DeviceInfo di;
+  if (device_info(&di)) return 1;
+  const bool b_mn = b_mn_major != 0;
+  const int kb1 = cdiv(K, lyco::GEMM_BLOCK_K), kb2 = cdiv(K2, lyco::GEMM_BLOCK_K);
+  const TileChoice tc = pick_tile(M, N, di.sms, 1, b_mn);
+  const int bn = tc.bn;
+  const int m_tiles = cdiv(M, tc.pair ? 256 : 128), n_tiles = cdiv(N, bn);
+  CUtensorMap ta, tb, ta2, tb2, tcm;
+  if (make_tmap(&ta, A, K, M, lda, 64, 128)) return 1;
+  if (make_tmap(&ta2, A2, K2, M, lda2, 64, 128)) return 1;
+  if (!b_mn) {
+    if (make_tmap(&tb, B, K, N, ldb, 64, tc.pair ? bn / 2 : bn)) return 1;
+    if (make_tmap(&tb2, B2, K2, N, ldb2, 64, tc.pair ? bn / 2 : bn)) return 1;
+  } else {
+    if (make_tmap(&tb, B, N, K, ldb, 64, 64)) return 1;
+    if (make_tmap(&tb2, B2, N, K2, ldb2, 64, 64)) return 1;
+  }
+  if (make_tmap_c(&tcm, C, N, M, ldc)) return 1;
+  lyco::GemmParams p;
+  p.C = C; p.bias = bias; p.ldc = ldc; p.M = M; p.N = N; p.K = K + K2;
+  p.m_tiles = m_tiles; p.n_tiles = n_tiles; p.splits = 1; p.k_blocks = kb1 + kb2; p.k_blocks1 = kb1;
+  p.block_n = bn; p.stages = stages_for(tc.pair, bn);
+  p.fmt = (dtype == LYCO_BF16) ? 1 : 0;
+  p.bias_dtype = bias_dtype;
+  p.epi_pq = 0;
+  const long total = static_cast<long>(m_tiles) * n_tiles;
+  const long slots = tc.pair ? di.sms / 2 : di.sms;
+  const int workers = static_cast<int>(total < slots ? total : slots);
+  const SidePair side{&ta2, &tb2};
+  if (tc.pair) return dispatch_gemm<true>(false, b_mn, lyco::EPI_STORE16, ta, tb, tcm, p, 2 * workers, stream, side);
+  return dispatch_gemm<false>(false, b_mn, lyco::EPI_STORE16, ta, tb, tcm, p, workers, stream, side);
 }
 
 int lyco_conv2d_fprop(const void* X, const void* Wk, void* Y, const void* bias, int bias_dtype, int Nb, int H,
@@ -510,7 +574,7 @@ int lyco_conv2d_fprop(const void* X, const void* Wk, void* Y, const void* bias, 
   cp.g.epi_pq = P * Q;
   cp.g.C = Y; cp.g.bias = bias; cp.g.ldc = O; cp.g.M = M; cp.g.N = O; cp.g.K = K;
   cp.g.m_tiles = cdiv(M, pair ? 256 : 128); cp.g.n_tiles = cdiv(O, bn); cp.g.splits = 1;
-  cp.g.k_blocks = R * S * (C / 64);
+  cp.g.k_blocks = R * S * (C / 64); cp.g.k_blocks1 = cp.g.k_blocks;
   cp.g.block_n = bn; cp.g.stages = stages_for(pair, bn);
   cp.g.fmt = (dtype == LYCO_BF16) ? 1 : 0; cp.g.bias_dtype = bias_dtype;
   cp.PQ = P * Q; cp.Q = Q; cp.C = C; cp.CB = C / 64; cp.S = S; cp.stride = stride;
@@ -631,6 +695,7 @@ int lyco_conv2d_wgrad(const void* X, const void* dY, float* dW, int Nb, int H, i
   const int ldw = taps * C;
   cp.g.C = dW; cp.g.bias = nullptr; cp.g.ldc = ldw; cp.g.M = O; cp.g.N = ldw; cp.g.K = Mpix;
   cp.g.m_tiles = m_tiles; cp.g.n_tiles = taps * tiles_per_tap; cp.g.splits = splits; cp.g.k_blocks = k_blocks;
+  cp.g.k_blocks1 = k_blocks;
   cp.g.block_n = bn; cp.g.stages = stages_for(pair, bn);
   cp.g.fmt = (dtype == LYCO_BF16) ? 1 : 0; cp.g.bias_dtype = 0;
   cp.PQ = P * Q; cp.Q = Q; cp.C = C; cp.CB = C / 64; cp.S = S; cp.stride = stride;
@@ -891,7 +956,7 @@ static int dora_check(const char* who, const void* Wm, int N, int K, int on_out,
 }
 
 int lyco_dora_fwd(const void* Wm, void* W_out, const float* dora_scale, float* sumsq, int N, int K, int on_out,
-                  int taps, float mult, float eps, int w_dtype, void* stream_) {
+                  int taps, float mult, float eps, int w_dtype, int scale_dtype, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (dora_check("lyco_dora_fwd", Wm, N, K, on_out, taps, w_dtype)) return 1;
   if (!W_out || !dora_scale || !sumsq) return fail("lyco_dora_fwd: null operand");
@@ -907,14 +972,15 @@ int lyco_dora_fwd(const void* Wm, void* W_out, const float* dora_scale, float* s
   const int64_t cap = static_cast<int64_t>(di.sms) * 16;
   if (grid > cap) grid = cap;
   lyco::dora_apply_fwd_kernel<<<static_cast<int>(grid), 256, 0, stream>>>(wm, static_cast<uint16_t*>(W_out), sumsq, dora_scale,
-                                                                         N, K, on_out, taps, mult, eps, w_dtype);
+                                                                         N, K, on_out, taps, mult, eps, w_dtype, scale_dtype);
   LYCO_CUDA(cudaGetLastError());
   g_launches.fetch_add(2, std::memory_order_relaxed);
   return 0;
 }
 
 int lyco_dora_bwd(float* dW, const void* Wm, const float* dora_scale, const float* sumsq, float* t, float* g_scale,
-                  int N, int K, int on_out, int taps, float mult, float eps, int w_dtype, void* stream_) {
+                  int N, int K, int on_out, int taps, float mult, float eps, int w_dtype, int scale_dtype,
+                  void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (dora_check("lyco_dora_bwd", Wm, N, K, on_out, taps, w_dtype)) return 1;
   if (!dW || !dora_scale || !sumsq || !t) return fail("lyco_dora_bwd: null operand");
@@ -931,7 +997,7 @@ int lyco_dora_bwd(float* dW, const void* Wm, const float* dora_scale, const floa
   if (grid > cap) grid = cap;
   if (grid * 256 < groups) grid = (groups + 255) / 256;  // the first `groups` threads also write g_scale
   lyco::dora_apply_bwd_kernel<<<static_cast<int>(grid), 256, 0, stream>>>(dW, wm, sumsq, dora_scale, t, g_scale, N, K, on_out,
-                                                                         taps, mult, eps, w_dtype, groups);
+                                                                         taps, mult, eps, w_dtype, groups, scale_dtype);
   LYCO_CUDA(cudaGetLastError());
   g_launches.fetch_add(2, std::memory_order_relaxed);
   return 0;

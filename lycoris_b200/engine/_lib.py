@@ -24,6 +24,7 @@ EXPORTED_SYMBOLS = (
     "lyco_device_check",
     "lyco_launch_count",
     "lyco_gemm",
+    "lyco_gemm_dual",
     "lyco_conv2d_fprop",
     "lyco_conv2d_wgrad",
     "lyco_transpose_cast",
@@ -94,6 +95,12 @@ def _bind(lib):
         c_int, c_int, c_int,  # M N K
         c_int, c_int, c_int, c_void_p,  # ab_dtype, split_k, accumulate, stream
     ]
+    lib.lyco_gemm_dual.restype = c_int
+    lib.lyco_gemm_dual.argtypes = [
+        c_void_p, c_int64, c_void_p, c_int, c_int64, c_int,  # A lda B b_mn ldb K
+        c_void_p, c_int64, c_void_p, c_int64, c_int,  # A2 lda2 B2 ldb2 K2
+        c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_void_p,  # C ldc bias bias_dtype M N dtype stream
+    ]
     lib.lyco_conv2d_fprop.restype = c_int
     lib.lyco_conv2d_fprop.argtypes = [
         c_void_p, c_void_p, c_void_p, c_void_p, c_int,  # X Wk Y bias bias_dtype
@@ -131,12 +138,12 @@ def _bind(lib):
     lib.lyco_delta_weight.argtypes = [POINTER(DeltaDesc), c_void_p, c_void_p, c_int, c_void_p, c_void_p]
     lib.lyco_dora_fwd.restype = c_int
     lib.lyco_dora_fwd.argtypes = [
-        c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_void_p,
+        c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_int, c_void_p,
     ]
     lib.lyco_dora_bwd.restype = c_int
     lib.lyco_dora_bwd.argtypes = [
         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,  # dW Wm dora_scale sumsq t g_scale
-        c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_void_p,
+        c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_int, c_void_p,
     ]
     return lib
 

@@ -101,6 +101,37 @@ def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, out_dtype=None, split_k=0, 
     return out
 
 
+def gemm_dual(a, b, a2, b2, *, b_mn=False, bias=None):
+    """``C[M,N] = A·Bᵀ + A2·B2ᵀ (+ bias)`` in ONE kernel / one TMEM accumulator (lyco_gemm_dual): ``a`` [M,K], ``a2``
+    [M,K2] row-major; ``b`` [N,K] and ``b2`` [N,K2] (``b_mn=False``) or ``b`` [K,N] and ``b2`` [K2,N] (``b_mn=True``)."""
+    _require_cuda(a, b, a2, b2, bias)
+    M, Kd = a.shape
+    K2 = a2.shape[1]
+    N = b.shape[1] if b_mn else b.shape[0]
+    if (b.shape[0] if b_mn else b.shape[1]) != Kd or (b2.shape[0] if b_mn else b2.shape[1]) != K2 or a2.shape[0] != M \
+            or (b2.shape[1] if b_mn else b2.shape[0]) != N:
+        raise ValueError(f"lycoris_b200.gemm_dual: shape mismatch {tuple(a.shape)} {tuple(b.shape)} {tuple(a2.shape)} {tuple(b2.shape)}")
+    if not (a.dtype == b.dtype == a2.dtype == b2.dtype):
+        raise TypeError("lycoris_b200.gemm_dual: operand dtypes differ")
+    out = torch.empty((M, N), device=a.device, dtype=a.dtype)
+    prof = _gemm_profile
+    if prof is not None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+    rc = _lib.load().lyco_gemm_dual(
+        _ptr(a), a.stride(0), _ptr(b), int(b_mn), b.stride(0), Kd,
+        _ptr(a2), a2.stride(0), _ptr(b2), b2.stride(0), K2,
+        _ptr(out), out.stride(0), _ptr(bias), dtype_code(bias.dtype) if bias is not None else 0, M, N,
+        dtype_code(a.dtype), _stream())
+    _lib.check(rc, "gemm_dual")
+    if prof is not None:
+        e1.record()
+        es = a.element_size()
+        prof.append((e0, e1, 2.0 * M * N * (Kd + K2), M, N, Kd + K2, float(es * (M * (Kd + K2) + N * (Kd + K2) + M * N))))
+    return out
+
+
 def conv2d_supported(x, weight_shape, stride, padding, dilation, groups, dtype=None) -> bool:
     """Geometry the implicit-GEMM kernels cover: 2-D, dilation 1, groups 1, C % 64 == 0, O % 8 == 0.
     (Activations must be NHWC; callers convert NCHW tensors with one transpose pass.)"""
@@ -323,7 +354,7 @@ def delta_weight(desc: DeltaDesc, shape, out_dtype=torch.float32, W=None, want_o
     return out, nsq
 
 
-def dora_fwd(Wm, dora_scale, on_out, taps, mult, eps):
+def dora_fwd(Wm, dora_scale, on_out, taps, mult, eps, scale_dtype=torch.float32):
     """``(W'', sumsq)`` — DoRA rescale of the merged 16-bit weight (lyco_dora_fwd)."""
     _require_cuda(Wm, dora_scale)
     N = Wm.shape[0]
@@ -333,12 +364,12 @@ def dora_fwd(Wm, dora_scale, on_out, taps, mult, eps):
     out = torch.empty_like(Wm)
     sumsq = torch.empty(groups, device=Wm.device, dtype=torch.float32)
     rc = _lib.load().lyco_dora_fwd(_ptr(Wm), _ptr(out), _ptr(dora_scale), _ptr(sumsq), N, K, int(on_out), int(taps),
-                                   float(mult), float(eps), dtype_code(Wm.dtype), _stream())
+                                   float(mult), float(eps), dtype_code(Wm.dtype), dtype_code(scale_dtype), _stream())
     _lib.check(rc, "dora_fwd")
     return out, sumsq
 
 
-def dora_bwd(dW, Wm, dora_scale, sumsq, on_out, taps, mult, eps, want_scale_grad=True):
+def dora_bwd(dW, Wm, dora_scale, sumsq, on_out, taps, mult, eps, want_scale_grad=True, scale_dtype=torch.float32):
     """In place: fp32 ``dW`` (gradient of W'') becomes the gradient of Wm; returns the fp32 gradient of dora_scale."""
     _require_cuda(dW, Wm)
     N = Wm.shape[0]
@@ -348,12 +379,12 @@ def dora_bwd(dW, Wm, dora_scale, sumsq, on_out, taps, mult, eps, want_scale_grad
     t = torch.empty(groups, device=dW.device, dtype=torch.float32)
     g = torch.empty(groups, device=dW.device, dtype=torch.float32) if want_scale_grad else None
     rc = _lib.load().lyco_dora_bwd(_ptr(dW), _ptr(Wm), _ptr(dora_scale), _ptr(sumsq), _ptr(t), _ptr(g), N, K, int(on_out),
-                                   int(taps), float(mult), float(eps), dtype_code(Wm.dtype), _stream())
+                                   int(taps), float(mult), float(eps), dtype_code(Wm.dtype), dtype_code(scale_dtype), _stream())
     _lib.check(rc, "dora_bwd")
     return g
 
 
 __all__ = [
-    "gemm", "gemm_supported", "conv2d_supported", "as_nhwc", "conv2d_fprop", "conv2d_wgrad", "make_desc", "merge_weight", "factor_grads", "dtype_code",
+    "gemm", "gemm_dual", "gemm_supported", "conv2d_supported", "as_nhwc", "conv2d_fprop", "conv2d_wgrad", "make_desc", "merge_weight", "factor_grads", "dtype_code",
     "grad_prep", "lokr_mix", "lokr_w1grad", "delta_weight", "dora_fwd", "dora_bwd", "ALGO_LOCON", "ALGO_LOHA", "ALGO_LOKR", "ALGO_IA3", "ALGO_DYLORA", "ALGO_RAW", "BF16", "F16", "F32",
 ]

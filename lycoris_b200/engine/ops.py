@@ -277,6 +277,73 @@ def _lowrank_grads(spec, factors, dWm, prod):
             K.gemm(G2, f[3], out_dtype=f32), K.gemm(f[2], G2, a_mn=True, b_mn=True, out_dtype=f32)]
 
 
+# ------------------------------------------------------- LoCon / DyLoRA side path (no merged weight)
+# y = x·Wᵀ + (x·downᵀ)·(s·up)ᵀ + b with BOTH products in one TMEM accumulator (lyco_gemm_dual): the adapter's rank-r
+# side path rides in the base contraction, W' is never formed, and backward needs no dense dW' — 2 dense contractions
+# per layer-step, the algorithmic minimum, instead of 3.  Contraction order = the reference's own bypass
+# path (locon.py:273-307); rebuild-mode rounding differs by the snap of dW onto W's grid.
+# LYCO_LOCON=merged keeps the round-1 merged-weight path.
+_LOCON_SIDE = os.environ.get("LYCO_LOCON", "side") != "merged"
+
+
+def _locon_side_ok(spec, conv, delta_only, W, x2, cdt):
+    return (_LOCON_SIDE and spec.algo in (K.ALGO_LOCON, K.ALGO_DYLORA) and conv is None and not delta_only
+            and spec.dora is None and spec.rank % 8 == 0 and 8 <= spec.rank <= 256
+            and W.dim() == 2 and W.shape[0] % 8 == 0 and W.shape[1] % 8 == 0
+            and x2.shape[0] > 0 and cdt in _HALF and K.gemm_supported(x2, W))
+
+
+class _LoconSidePath(torch.autograd.Function):
+    """Linear LoCon / DyLoRA without a merged weight (see _LOCON_SIDE)."""
+
+    @staticmethod
+    def forward(ctx, x, W, bias, spec, up, down):
+        cdt = W.dtype
+        s = spec.m_pre * spec.m_post1 * spec.m_post2
+        down_c = (down * spec.m_in if (spec.algo == K.ALGO_DYLORA and spec.m_in != 1.0) else down).to(cdt).contiguous()
+        up_s = (up * s if s != 1.0 else up).to(cdt).contiguous()            # [N, r]: the scale chain folded into `up`
+        x2 = x.reshape(-1, x.shape[-1])
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        T = K.gemm(x2, down_c)                                               # [M, r] = x·downᵀ
+        y = K.gemm_dual(x2, W, T, up_s, bias=bias).view(*x.shape[:-1], W.shape[0])
+        ctx.save_for_backward(x, W, T, up_s, down_c)
+        ctx.spec, ctx.scale, ctx.f_dtypes = spec, s, (up.dtype, down.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W, T, up_s, down_c = ctx.saved_tensors
+        spec = ctx.spec
+        N = W.shape[0]
+        dy2 = dy.reshape(-1, N)
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        need_x = ctx.needs_input_grad[0]
+        need_up, need_down = ctx.needs_input_grad[4], ctx.needs_input_grad[5]
+        dx = g_up = g_down = None
+        f32 = torch.float32
+        U = K.gemm(dy2, up_s, b_mn=True) if (need_x or need_down) else None  # [M, r] = dY·(s·up)
+        if need_x:
+            dx = K.gemm_dual(dy2, W, U, down_c, b_mn=True).view(x.shape)     # dY·W + U·down
+        if need_up:
+            g_up = K.gemm(dy2, T, a_mn=True, b_mn=True, out_dtype=f32)       # dYᵀ·T   [N, r]
+            if ctx.scale != 1.0:
+                g_up = g_up * ctx.scale
+        if need_down:
+            x2 = x.reshape(-1, x.shape[-1])
+            if not x2.is_contiguous():
+                x2 = x2.contiguous()
+            g_down = K.gemm(U, x2, a_mn=True, b_mn=True, out_dtype=f32)      # Uᵀ·X    [r, K]
+            if spec.algo == K.ALGO_DYLORA and spec.m_in != 1.0:
+                g_down = g_down * spec.m_in
+        if g_up is not None and g_up.dtype != ctx.f_dtypes[0]:
+            g_up = g_up.to(ctx.f_dtypes[0])
+        if g_down is not None and g_down.dtype != ctx.f_dtypes[1]:
+            g_down = g_down.to(ctx.f_dtypes[1])
+        return dx, None, None, None, g_up, g_down
+
+
 # ------------------------------------------------------- structured LoKr factor gradients
 # dW = kron(w1, w2): g_w1 / g_w2 from two skinny contractions (1/uq of the dense FLOPs each) instead of the dense
 # fp32 dW' = dYᵀ·X + a reduction pass over it (lokr_struct_kernels.cuh).  LYCO_LOKR_GRAD=dense keeps the round-1 path.
@@ -342,7 +409,8 @@ class _AdapterContraction(torch.autograd.Function):
         for d_ in W.shape[2:]:
             taps *= d_
         # eps is that of the dtype the reference computes the norm in (= dora_scale's: fp32, or bf16 for a bf16 adapter)
-        return g.detach().reshape(-1).float().contiguous(), bool(on_out), taps, float(mult), float(torch.finfo(g.dtype).eps)
+        return (g.detach().reshape(-1).float().contiguous(), bool(on_out), taps, float(mult), float(torch.finfo(g.dtype).eps),
+                g.dtype if g.dtype in _HALF else torch.float32)
 
     @staticmethod
     def forward(ctx, x, W, bias, spec, conv, delta_only, ac_dtype, dora_scale, *factors):
@@ -352,8 +420,8 @@ class _AdapterContraction(torch.autograd.Function):
         Wm = _AdapterContraction._merge(spec, factors_u, W, ac_dtype, out_dim, in_dim)
         sumsq = None
         if spec.dora is not None:
-            g32, on_out, taps, mult, eps = _AdapterContraction._dora_args(spec, W)
-            Wm, sumsq = K.dora_fwd(Wm, g32, on_out, taps, mult, eps)  # the pre-rescale W + dW is recomputed in backward
+            g32, on_out, taps, mult, eps, sdt = _AdapterContraction._dora_args(spec, W)
+            Wm, sumsq = K.dora_fwd(Wm, g32, on_out, taps, mult, eps, sdt)  # the pre-rescale W + dW is recomputed in backward
         if delta_only:
             Wm = Wm - W  # exact on W's grid: this is the reference's `new_weight - base_weight`
         if conv is None:
@@ -405,10 +473,10 @@ class _AdapterContraction(torch.autograd.Function):
                 dWm = dWm.contiguous()
                 if spec.dora is not None:
                     # gradient of W'' -> gradient of W + dW (in place) and of dora_scale
-                    g32, on_out, taps, mult, eps = _AdapterContraction._dora_args(spec, W)
+                    g32, on_out, taps, mult, eps, sdt = _AdapterContraction._dora_args(spec, W)
                     Wpre = _AdapterContraction._merge(spec, factors_u, W, ctx.ac_dtype, out_dim, in_dim)
                     g_dora = K.dora_bwd(dWm, Wpre, g32, sumsq, on_out, taps, mult, eps,
-                                        want_scale_grad=ctx.needs_input_grad[NF - 1])
+                                        want_scale_grad=ctx.needs_input_grad[NF - 1], scale_dtype=sdt)
                     if g_dora is not None:
                         ds = spec.dora[0]
                         g_dora = g_dora.view(ds.shape).to(ds.dtype)
@@ -556,6 +624,10 @@ def adapter_forward(module, x, args, kwargs, native_spec, assemble_fallback):
         base = module.org_forward(x, *args, **kwargs)
 
     spec = native_spec()
+    if spec is not None and plain and _locon_side_ok(spec, conv, False, W, x.reshape(-1, x.shape[-1]), cdt):
+        up, down = spec.factors
+        y = _LoconSidePath.apply(x, W, bias, spec, up, down)
+        return y
     if spec is not None:
         y = _AdapterContraction.apply(x, W, None if not plain else bias, spec, conv, not plain, ac,
                                       spec.dora[0] if spec.dora is not None else None, *spec.factors)

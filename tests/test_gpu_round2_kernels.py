@@ -127,6 +127,92 @@ def test_structured_path_is_taken_and_launches_fewer_flops():
     assert (160, 160, 2048 * 8) in shapes and (2048 * 8, 160, 160) in shapes, shapes
 
 
+# ------------------------------------------------------------------------------------------ LoCon side path
+@pytest.mark.parametrize("M,N,K,K2,b_mn", [(1024, 1280, 1280, 16, False), (1024, 1280, 1280, 16, True), (300, 640, 320, 8, False),
+                                           (8192, 10240, 1280, 64, False), (616, 1280, 2048, 32, True), (64, 96, 64, 8, False)])
+def test_gemm_dual_kernel(M, N, K, K2, b_mn):
+    """C = A·Bᵀ + A2·B2ᵀ + bias in one accumulator vs fp32 matmuls of the same bf16 operands."""
+    from lycoris_b200.engine import kernels as Kk
+
+    g = torch.Generator().manual_seed(0)
+    a = torch.randn(M, K, generator=g).cuda().to(torch.bfloat16)
+    a2 = torch.randn(M, K2, generator=g).cuda().to(torch.bfloat16)
+    b = (torch.randn(N, K, generator=g) * 0.05).cuda().to(torch.bfloat16)
+    b2 = (torch.randn(N, K2, generator=g) * 0.05).cuda().to(torch.bfloat16)
+    bias = None if b_mn else torch.randn(N, generator=g).cuda().to(torch.bfloat16)
+    ref = a.float() @ b.float().t() + a2.float() @ b2.float().t()
+    if bias is not None:
+        ref = ref + bias.float()
+    if b_mn:
+        out = Kk.gemm_dual(a, b.t().contiguous(), a2, b2.t().contiguous(), b_mn=True)
+    else:
+        out = Kk.gemm_dual(a, b, a2, b2, bias=bias)
+    assert out.shape == (M, N) and out.dtype == torch.bfloat16
+    assert float((out.float() - ref).abs().max()) <= 2.0 ** -7 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("algo", ["locon", "dylora"])
+@pytest.mark.parametrize("M,N,K,r", [(2048, 1280, 1280, 16), (8192, 10240, 1280, 16), (616, 1280, 2048, 32), (256, 640, 320, 8)])
+def test_locon_side_path_matches_merged_path_and_fp64(algo, M, N, K, r):
+    """LoCon / DyLoRA on nn.Linear: y = x·Wᵀ + (x·downᵀ)(s·up)ᵀ in one accumulator, no W', no dense dW' — against the
+    round-1 merged-weight path on the same layer and against an fp64 evaluation of the same formula."""
+    import random
+
+    import lycoris_b200 as L
+    from lycoris_b200.engine import kernels as Kk
+    from lycoris_b200.engine import ops
+
+    torch.manual_seed(0)
+    base = nn.Linear(K, N).cuda().to(torch.bfloat16)
+    base.requires_grad_(False)
+    if algo == "locon":
+        mod = L.LoConModule("t", base, 0.8, r, r / 2).cuda()
+        with torch.no_grad():
+            mod.lora_up.weight.normal_(0, 0.05)
+    else:
+        mod = L.DyLoraModule("t", base, 0.8, r, r / 2, block_size=r // 2).cuda()
+        with torch.no_grad():
+            for u in mod.up_list:
+                u.normal_(0, 0.05)
+    gen = torch.Generator().manual_seed(3)
+    x = torch.randn(M, K, generator=gen).cuda().to(torch.bfloat16)
+    dy = (torch.randn(M, N, generator=gen) * 0.1).cuda().to(torch.bfloat16)
+    mod.apply_to()
+    mod.train()
+
+    def run(side):
+        saved = ops._LOCON_SIDE
+        ops._LOCON_SIDE = side
+        sink = []
+        Kk.set_gemm_profiler(sink)
+        try:
+            for p in mod.parameters():
+                p.grad = None
+            random.seed(5)  # DyLoRA: the same block on both paths (block_count = 2: rank r/2 or r)
+            xe = x.clone().requires_grad_(True)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                y = base(xe)
+            y.backward(dy)
+            grads = {k: p.grad.clone() for k, p in mod.named_parameters() if p.grad is not None}
+            return y.detach(), xe.grad, grads, sorted((r_[3], r_[4], r_[5]) for r_ in sink)
+        finally:
+            Kk.set_gemm_profiler(None)
+            ops._LOCON_SIDE = saved
+
+    ys, dxs, gs, shapes_s = run(True)
+    ym, dxm, gm, shapes_m = run(False)
+    mod.restore()
+    live_rank = [s_ for s_ in shapes_s if s_[1] <= r and s_[0] == M]  # T = x·downᵀ : (M, rank, K)
+    if live_rank and live_rank[0][1] % 8 == 0:
+        assert (N, K, M) not in shapes_s, "dense dW' contraction launched on the side path"
+        assert (N, K, M) in shapes_m
+    assert float((ys.float() - ym.float()).abs().max()) <= 2.0 ** -6 * float(ym.float().abs().max())
+    assert float((dxs.float() - dxm.float()).abs().max()) <= 2.0 ** -6 * float(dxm.float().abs().max())
+    assert set(gs) == set(gm)
+    for k_ in gm:
+        assert rel_err(gs[k_], gm[k_]) <= 3e-2, (k_, rel_err(gs[k_], gm[k_]))
+
+
 # ------------------------------------------------------------------------------------------ delta weight
 def _mods(dtype):
     import lycoris_b200 as L
