@@ -156,23 +156,49 @@ __global__ void __launch_bounds__(256) lokr_w1grad_kernel(const uint16_t* __rest
       }
     }
   }
-  __shared__ float red[NA * NB];
-  for (int i = threadIdx.x; i < NA * NB; i += blockDim.x) red[i] = 0.f;
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
+  // Reduction of the NA*NB per-lane partial sums.  Butterfly over the VALUE index: at each step a lane keeps one half
+  // of its values and hands the other half to its partner (NA*NB - 2 shuffles in total instead of 5 per value), so
+  // after five steps lane l holds the warp totals of values {2*rev(l), 2*rev(l)+1}.  Warp totals go to a per-warp row
+  // of shared memory (plain stores — shared-memory float atomics are CAS loops), 64 threads add the 8 rows and issue
+  // ONE global atomic per entry per CTA.
+  constexpr int NV = NA * NB;
+  static_assert(NV == 64 || NV == 16, "value count handled by the butterfly below");
+  float v[NV];
 #pragma unroll
   for (int a = 0; a < NA; ++a)
 #pragma unroll
-    for (int b = 0; b < NB; ++b) {
-      float s = acc[a][b];
+    for (int b = 0; b < NB; ++b) v[a * NB + b] = acc[a][b];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int base = 0;  // index of v[0] after the steps so far
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) atomicAdd(&red[a * NB + b], s);
+  for (int off = 16, n = NV; off >= 1 && n >= 2; off >>= 1, n >>= 1) {
+    const int half = n >> 1;
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = upper ? v[i] : v[i + half];
+      const float keep = upper ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
     }
+    if (upper) base += half;
+  }
+  // NV = 64: five steps leave 2 values per lane; NV = 16: four steps (off 16..2) leave 1 value per lane PAIR member —
+  // handle generically: `left` values per lane, lanes that differ only in the unused low offset bits hold duplicates
+  constexpr int STEPS = (NV == 64) ? 5 : 4;
+  constexpr int left = NV >> STEPS;
+  if (NV == 16) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);  // the offset the 16-value butterfly did not use
+  __shared__ float red[8][NV];
+  if (NV == 64 || (lane & 1) == 0) {
+#pragma unroll
+    for (int i = 0; i < left; ++i) red[warp][base + i] = v[i];
+  }
   __syncthreads();
-  for (int i = threadIdx.x; i < NA * NB; i += blockDim.x) {
+  for (int i = threadIdx.x; i < NV; i += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][i];
     const int a = i / NB, b = i % NB;
-    if (a < na && b < nb) atomicAdd(&g[a * nb + b], red[i] * gscale);
+    if (a < na && b < nb) atomicAdd(&g[a * nb + b], s * gscale);
   }
 }
 

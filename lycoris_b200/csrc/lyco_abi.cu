@@ -62,6 +62,14 @@ struct DeviceInfo {
 // processes and device switches stay correct
 int device_info(DeviceInfo* out) {
   static DeviceInfo cache[64];
+  // The tensor-map encoders are DRIVER entry points and need a current context on the calling thread.  A thread that
+  // has made no runtime call yet (autograd's backward worker when an engine node is the FIRST node it runs) has none:
+  // cuTensorMapEncodeTiled then fails with CUDA_ERROR_INVALID_CONTEXT (201).  cudaFree(0) binds the primary context.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    LYCO_CUDA(cudaFree(nullptr));
+    ctx_bound = true;
+  }
   int dev = 0;
   LYCO_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) return fail("device index %d out of range", dev);
@@ -431,10 +439,23 @@ int lyco_gemm(const void* A, int a_mn_major, int64_t lda, const void* B, int b_m
     if (force_choice(&forced, b_mn)) {
       tc = forced;
     } else {
-      tc.pair = M > 128 && pair_enabled();
-      tc.bn = 256;
-      while (tc.bn > 32 && tc.bn - (b_mn ? (tc.pair ? 128 : 64) : 32) >= N) tc.bn -= b_mn ? (tc.pair ? 128 : 64) : 32;
-      if (!tile_valid(tc.pair, tc.bn, b_mn)) { tc.pair = false; tc.bn = b_mn ? 64 : 32; }
+      // widest tile that covers N, as a CTA pair (256 rows) or a single CTA (128 rows): take the variant that pads
+      // the [M, N] output less per unit of tile throughput — a 160 x 160 output (the structured LoKr g_w2) is 39 %
+      // useful MMA work in a 256 x 256 pair tile, 52 % in two 128 x 192 single-CTA tiles, which also split the
+      // reduction over all 148 SMs instead of 74 pairs
+      double best = 1e30;
+      for (int pr = 1; pr >= 0; --pr) {
+        if (pr && (M <= 128 || !pair_enabled())) continue;
+        const int step = b_mn ? (pr ? 128 : 64) : 32;
+        int bn = 256;
+        while (bn > step && bn - step >= N) bn -= step;
+        if (!tile_valid(pr, bn, b_mn)) continue;
+        const int rows = pr ? 256 : 128;
+        const double padded = static_cast<double>(cdiv(M, rows)) * rows * cdiv(N, bn) * bn;
+        const double cost = padded * tile_cost(pr, bn) / (128.0 * bn);
+        if (cost < best * 0.97) { best = cost; tc.pair = pr != 0; tc.bn = bn; }
+      }
+      if (best > 1e29) { tc.pair = false; tc.bn = b_mn ? 64 : 32; }
     }
     const long tiles = static_cast<long>(cdiv(M, tc.pair ? 256 : 128)) * cdiv(N, tc.bn);
     splits = split_k > 0 ? split_k : pick_splits(tiles, k_blocks, tc.pair ? di.sms / 2 : di.sms);

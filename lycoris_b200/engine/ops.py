@@ -346,12 +346,24 @@ class _LoconSidePath(torch.autograd.Function):
 
 # ------------------------------------------------------- structured LoKr factor gradients
 # dW = kron(w1, w2): g_w1 / g_w2 from two skinny contractions (1/uq of the dense FLOPs each) instead of the dense
-# fp32 dW' = dYᵀ·X + a reduction pass over it (lokr_struct_kernels.cuh).  LYCO_LOKR_GRAD=dense keeps the round-1 path.
-_LOKR_STRUCT = os.environ.get("LYCO_LOKR_GRAD", "structured") != "dense"
+# fp32 dW' = dYᵀ·X + a reduction pass over it (lokr_struct_kernels.cuh).  The structured form trades FLOPs for HBM
+# passes (≈4 over the smaller activation + 1 over the larger), so it is used where that pays — measured on B200:
+# layers with max(N, K) >= 4·min(N, K) (the feed-forward projections: 166 -> ~100 us at 10240x1280, M = 8192); square
+# layers (1280², 640²) stay on the dense tensor-core wgrad, which is faster there (45 vs ~55 us).
+# LYCO_LOKR_GRAD = auto (default) | all (every eligible layer) | dense (round-1 path everywhere).
+_LOKR_STRUCT = os.environ.get("LYCO_LOKR_GRAD", "auto")
+_LOKR_STRUCT_ASPECT = 4
 
 
 def _lokr_structured_ok(spec, conv, x2, dy2):
-    return (_LOKR_STRUCT and spec.algo == K.ALGO_LOKR and conv is None and spec.dora is None
+    mode = _LOKR_STRUCT
+    if mode in (False, "dense") or spec.algo != K.ALGO_LOKR:
+        return False
+    if mode not in (True, "all"):
+        n_out, n_in = spec.up * spec.vp, spec.uq * spec.vq
+        if max(n_out, n_in) < _LOKR_STRUCT_ASPECT * min(n_out, n_in):
+            return False
+    return (conv is None and spec.dora is None
             and 1 <= spec.up <= 8 and 1 <= spec.uq <= 8 and spec.vp % 8 == 0 and spec.vq % 8 == 0
             and x2.shape[0] > 0 and x2.dtype in _HALF and dy2.dtype == x2.dtype
             and x2.is_contiguous() and dy2.is_contiguous() and x2.data_ptr() % 16 == 0 and dy2.data_ptr() % 16 == 0)

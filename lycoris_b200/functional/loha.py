@@ -43,10 +43,10 @@ class _HadamardOfTuckers(torch.autograd.Function):
         return _tucker_full(t1, d1, u1) * _tucker_full(t2, d2, u2) * gamma
 
     @staticmethod
-    def _side_grads(g_full, t, d, u):
-        # g_full: gradient w.r.t. the rebuilt [p, r, ...] tensor of this side
-        half = torch.einsum("i j ..., j r -> i r ...", t, d)  # [i, r, ...]
-        g_u = torch.einsum("i r ..., p r ... -> i p", half, g_full)
+    def _side_grads(g_full, t, d, u, half_for_up):
+        """Gradients of one Tucker triple from ``g_full`` (gradient w.r.t. its rebuilt [p, r, ...] tensor).
+        ``half_for_up`` is the (core x down) product the UP gradient is contracted with — see backward()."""
+        g_u = torch.einsum("i r ..., p r ... -> i p", half_for_up, g_full)
         g_half = torch.einsum("p r ..., i p -> i r ...", g_full, u)
         g_d = torch.einsum("i j ..., i r ... -> j r", t, g_half)
         g_t = torch.einsum("i r ..., j r -> i j ...", g_half, d)
@@ -56,10 +56,17 @@ class _HadamardOfTuckers(torch.autograd.Function):
     def backward(ctx, g):
         t1, d1, u1, t2, d2, u2, gamma = ctx.saved_tensors
         g = g * gamma
-        g1 = g * _tucker_full(t2, d2, u2)
-        gt1, gd1, gu1 = _HadamardOfTuckers._side_grads(g1, t1, d1, u1)
-        g2 = g * _tucker_full(t1, d1, u1)
-        gt2, gd2, gu2 = _HadamardOfTuckers._side_grads(g2, t2, d2, u2)
+        half1 = torch.einsum("i j ..., j r -> i r ...", t1, d1)
+        half2 = torch.einsum("i j ..., j r -> i r ...", t2, d2)
+        g1 = g * torch.einsum("i r ..., i p -> p r ...", half2, u2)
+        g2 = g * torch.einsum("i r ..., i p -> p r ...", half1, u1)
+        # REFERENCE QUIRK, reproduced (never silently fixed — DESIGN §4): upstream's HadaWeightTucker.backward
+        # (lycoris/functional/loha.py:48-54, 62-68) contracts grad_w1u with the OTHER branch's half product
+        # (t2 x w2d) and grad_w2u with (t1 x w1d); the mathematically exact gradient would use the branch's own
+        # half.  Training dynamics of a LoHa-Tucker adapter depend on it, so parity with the reference's outputs
+        # (tests/golden/tucker_*.pt) requires the same contraction.
+        gt1, gd1, gu1 = _HadamardOfTuckers._side_grads(g1, t1, d1, u1, half_for_up=half2)
+        gt2, gd2, gu2 = _HadamardOfTuckers._side_grads(g2, t2, d2, u2, half_for_up=half1)
         return gt1, gd1, gu1, gt2, gd2, gu2, None
 
 

@@ -266,9 +266,11 @@ def test_cfg5_mixed_preset_network_matches_oracle_network():
     rec = {"loss_rel": abs(loss - ref_loss) / abs(ref_loss), "out": rel_err(out, ref_out), "dx": rel_err(dx, ref_dx),
            "g_median": statistics.median(errs.values()), "g_worst": max(errs.values())}
     _log("network/cfg5_toy", rec)
-    assert rec["loss_rel"] <= 2e-2 and rec["out"] <= 3e-2 and rec["dx"] <= 6e-2, rec
+    # measured on B200: loss 7e-5, out 1.3e-2, dx 2.0e-2, gradient median 2.3e-2, worst 3.5e-2 (the round-1 bound on the
+    # worst parameter gradient of the toy network was 0.25)
+    assert rec["loss_rel"] <= 5e-3 and rec["out"] <= 3e-2 and rec["dx"] <= 4e-2, rec
     assert rec["g_median"] <= 5e-2, rec
-    assert rec["g_worst"] <= 0.25, (rec, max(errs.items(), key=lambda kv: kv[1]))
+    assert rec["g_worst"] <= 0.1, (rec, max(errs.items(), key=lambda kv: kv[1]))
 
 
 # --------------------------------------------------------------------------- dropout on the GPU

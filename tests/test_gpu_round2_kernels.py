@@ -105,26 +105,42 @@ def test_structured_lokr_grads_match_dense_path(M, N, K, scale):
         assert ed <= 1e-2, (tag, "dense vs fp64", ed)
 
 
-def test_structured_path_is_taken_and_launches_fewer_flops():
+@pytest.mark.parametrize("mode,N,K,expect_structured", [("all", 1280, 1280, True), ("auto", 1280, 1280, False),
+                                                         ("auto", 5120, 1280, True), ("auto", 1280, 5120, True),
+                                                         ("dense", 5120, 1280, False)])
+def test_structured_path_selection(mode, N, K, expect_structured):
+    """LYCO_LOKR_GRAD: `auto` takes the structured contractions where they pay (max(N,K) >= 4 min(N,K): the feed-forward
+    projections) and the dense tensor-core wgrad on square layers; `all` / `dense` force one path."""
     import lycoris_b200 as L
-    from lycoris_b200.engine import kernels as K
+    from lycoris_b200.engine import kernels as K_
+    from lycoris_b200.engine import ops
 
     torch.manual_seed(0)
-    base = nn.Linear(1280, 1280).cuda().to(torch.bfloat16)
+    base = nn.Linear(K, N).cuda().to(torch.bfloat16)
     base.requires_grad_(False)
     mod = L.LokrModule("t", base, 1.0, 100000, 1, factor=8).cuda()
-    x = torch.randn(2048, 1280, device="cuda", dtype=torch.bfloat16)
+    M = 2048
+    x = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
     mod.apply_to()
     sink = []
-    K.set_gemm_profiler(sink)
-    with torch.autocast("cuda", dtype=torch.bfloat16):
-        y = base(x)
-    y.float().pow(2).mean().backward()
-    K.set_gemm_profiler(None)
-    mod.restore()
+    saved = ops._LOKR_STRUCT
+    ops._LOKR_STRUCT = mode
+    K_.set_gemm_profiler(sink)
+    try:
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = base(x)
+        y.float().pow(2).mean().backward()
+    finally:
+        K_.set_gemm_profiler(None)
+        ops._LOKR_STRUCT = saved
+        mod.restore()
     shapes = sorted((r[3], r[4], r[5]) for r in sink)
-    assert (1280, 1280, 2048) not in shapes, "dense dW' contraction still launched"
-    assert (160, 160, 2048 * 8) in shapes and (2048 * 8, 160, 160) in shapes, shapes
+    dense_wgrad = (N, K, M)
+    skinny = (N // 8, K // 8, M * 8)
+    if expect_structured:
+        assert dense_wgrad not in shapes and skinny in shapes, shapes
+    else:
+        assert dense_wgrad in shapes and skinny not in shapes, shapes
 
 
 # ------------------------------------------------------------------------------------------ LoCon side path
