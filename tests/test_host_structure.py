@@ -260,3 +260,39 @@ def test_out_of_scope_checkpoint_entries_warn_instead_of_loading_silently(caplog
     assert cls.__name__ == "LoConModule"
     text = " ".join(r.getMessage() for r in caplog.records)
     assert "Full adapter" in text and "Diag-OFT/BOFT" in text
+
+
+def test_quantised_style_base_is_forced_into_bypass_mode():
+    """a base layer that is a Linear SUBCLASS (what bitsandbytes / quanto layers are — their `.weight` is
+    not a dense 16-bit matrix) must never reach the merged-weight engine path: the adapter goes to bypass mode
+    (reference base.py:162-177), whose forward only calls `org_forward` and the adapter's own small layers."""
+    import torch
+    import torch.nn as nn
+
+    import lycoris_b200 as L
+
+    class FakeQuantLinear(nn.Linear):  # dequantises on the fly; reading .weight directly would be wrong
+        def forward(self, x):
+            return nn.functional.linear(x, self.weight.detach().round(decimals=2), self.bias)
+
+    torch.manual_seed(0)
+    base = FakeQuantLinear(32, 48)
+    base.requires_grad_(False)
+    for cls, kw in ((L.LoConModule, {}), (L.LokrModule, {"factor": 4}), (L.LohaModule, {})):
+        mod = cls("q", base, 1.0, 4, 2, **kw)
+        assert mod.bypass_mode and mod.is_quant, cls.__name__
+        with torch.no_grad():
+            for p in mod.parameters():
+                if float(p.abs().sum()) == 0.0:
+                    p.normal_(0, 0.05)
+        mod.apply_to()
+        x = torch.randn(5, 32, requires_grad=True)
+        y = base(x)  # CPU tensors: the rebuild-mode engine would raise EngineUnavailable; bypass is plain PyTorch
+        want = FakeQuantLinear.forward(base, x) + mod.bypass_forward_diff(x, scale=mod.multiplier)
+        assert torch.allclose(y, want, atol=1e-6), cls.__name__
+        y.pow(2).mean().backward()
+        assert all(p.grad is not None for p in mod.parameters()), cls.__name__
+        mod.restore()
+    # an explicit bypass_mode=False on a subclass is honoured (the user vouches for a dense weight)
+    mod = L.LoConModule("q2", base, 1.0, 4, 2, bypass_mode=False)
+    assert mod.bypass_mode is False and not mod.is_quant
