@@ -760,7 +760,17 @@ int lyco_merge_weight(const lyco_delta_desc_t* d, const void* W, void* W_out, vo
       const bool f32_bf16 = !generic_only && d->f_dtype == LYCO_F32 && d->w_dtype == LYCO_BF16 && !d->pre_round;
       const bool all_bf16 = !generic_only && d->f_dtype == LYCO_BF16 && d->w_dtype == LYCO_BF16 && d->pre_round &&
                             d->pre_dtype == LYCO_BF16;
-      if (vec && f32_bf16)
+      // row-blocked kernels (LYCO_MERGE_ROWS=0 keeps the element-indexed ones for the bit-exactness A/B)
+      static const bool rows_on = []() { const char* e = getenv("LYCO_MERGE_ROWS"); return !(e && *e == '0'); }();
+      const bool rows_ok = rows_on && vec && d->in_dim % 8 == 0 &&
+                           (reinterpret_cast<uintptr_t>(d->f1) & 15) == 0;
+      int rgrid = (d->out_dim + 7) / 8;  // 8 warps (rows) per CTA
+      if (rgrid > cap) rgrid = cap;
+      if (rows_ok && f32_bf16)
+        lyco::merge_lokr_rows_kernel<LYCO_F32, LYCO_BF16, lyco::PD_NONE><<<rgrid, 256, 0, stream>>>(*d, w, wo);
+      else if (rows_ok && all_bf16)
+        lyco::merge_lokr_rows_kernel<LYCO_BF16, LYCO_BF16, LYCO_BF16><<<rgrid, 256, 0, stream>>>(*d, w, wo);
+      else if (vec && f32_bf16)
         lyco::merge_lokr_kernel<8, LYCO_F32, LYCO_BF16, lyco::PD_NONE><<<grid, 256, 0, stream>>>(*d, w, wo);
       else if (vec && all_bf16)
         lyco::merge_lokr_kernel<8, LYCO_BF16, LYCO_BF16, LYCO_BF16><<<grid, 256, 0, stream>>>(*d, w, wo);

@@ -222,6 +222,72 @@ __global__ void __launch_bounds__(256) merge_lokr_kernel(lyco_delta_desc_t d, co
   }
 }
 
+// Row-blocked LoKr merge (round 2): one warp walks one weight row at a time, lanes stride over its 16-byte vectors.
+// The row decomposition (pu, pv) — two integer divisions in the element-indexed kernel above — is done once per row
+// per warp, the 8 values of w2 a vector needs arrive as two 16-byte loads (fp32 factors) or one (16-bit factors)
+// instead of eight scalar loads, the w1 row sits in registers / L1, and multipliers equal to 1 skip their rounding
+// step (bit-identical: rnd(x * 1) == x once x is on the grid).  Needs vq % 8 == 0 and 16-byte aligned arrays.
+template <int FD, int WD, int PD>
+__global__ void __launch_bounds__(256) merge_lokr_rows_kernel(lyco_delta_desc_t d, const uint16_t* __restrict__ W,
+                                                              uint16_t* __restrict__ Wout) {
+  constexpr int f_dtype = FD, w_dtype = WD;
+  constexpr int pre_round = PD == PD_NONE ? 0 : 1;
+  constexpr int pre_dtype = PD == PD_NONE ? LYCO_F32 : PD;
+  constexpr int fround = pre_round ? pre_dtype : LYCO_F32;
+  const int K = d.in_dim, N = d.out_dim, vq = d.vq, vp = d.vp, uq = d.uq;
+  const int kv = K >> 3;                     // 16-byte vectors per row
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const bool unit_pre = d.m_pre == 1.f, unit_p1 = d.m_post1 == 1.f, unit_p2 = d.m_post2 == 1.f;
+  for (int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; n < N; n += warps) {
+    const int pu = n / vp, pv = n - pu * vp;
+    const uint4* wrow = reinterpret_cast<const uint4*>(W + static_cast<int64_t>(n) * K);
+    uint4* orow = reinterpret_cast<uint4*>(Wout + static_cast<int64_t>(n) * K);
+    // two vectors per lane per trip: both weight loads are issued before either is consumed
+    for (int i0 = lane; i0 < kv; i0 += 64) {
+      const int i1 = i0 + 32;
+      const bool has1 = i1 < kv;
+      const uint4 wv0 = __ldg(wrow + i0);
+      const uint4 wv1 = has1 ? __ldg(wrow + i1) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        if (t == 1 && !has1) break;
+        const int i = t ? i1 : i0;
+        const uint4 wv = t ? wv1 : wv0;
+        const int k = i << 3;
+        const int u = k / vq, v = k - u * vq;
+        const float a = rnd(ld_f(d.f0, f_dtype, pu * uq + u), fround);
+        float b[8];
+        const int64_t boff = static_cast<int64_t>(pv) * vq + v;
+        if (f_dtype == LYCO_F32) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(d.f1) + boff));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(d.f1) + boff) + 1);
+          b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+        } else {
+          const uint4 bv = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(d.f1) + boff));
+          const uint16_t* bh = reinterpret_cast<const uint16_t*>(&bv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) b[j] = cvt16(bh[j], f_dtype);
+        }
+        const uint16_t* wh = reinterpret_cast<const uint16_t*>(&wv);
+        uint4 ov;
+        uint16_t* oh = reinterpret_cast<uint16_t*>(&ov);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          // the rounding chain of apply_chain(), with the identity steps folded away
+          float dv = rnd(a * rnd(b[j], fround), fround);
+          if (!unit_pre) dv = rnd(dv * d.m_pre, fround);
+          dv = rnd(dv, w_dtype);
+          if (!unit_p1) dv = rnd(dv * d.m_post1, w_dtype);
+          if (!unit_p2) dv = rnd(dv * d.m_post2, w_dtype);
+          oh[j] = to16(cvt16(wh[j], w_dtype) + dv, w_dtype);
+        }
+        orow[i] = ov;
+      }
+    }
+  }
+}
+
 // RAW: the rank-r products were formed on the tensor cores (lyco_gemm with K = r) and arrive as 16-bit
 // [N, K'] arrays: W' = rnd(W + chain(raw1 [* raw2])).  Used for LoCon / DyLoRA (one product) and LoHa (two).
 // D16 != DT_RUNTIME: products, product domain and weights all in that 16-bit dtype (the autocast / all-bf16 regimes).
