@@ -27,6 +27,17 @@ def main():
         k.conv2d_fprop(xs, wk, None, 3, 3, (1, 1), 1)                                       # NHWC epilogue
         k.conv2d_fprop(xs, wk, None, 3, 3, (1, 1), 1, out_nchw=True)                        # NCHW, TMA stores
         k.conv2d_fprop(xs, wd, None, 3, 3, (1, 1), 1, out_nchw=True, out_dtype=torch.float32)  # NCHW fp32
+    # round 2: DoRA rescale around the merged weight and the standalone delta weight, at the GEGLU projection's size
+    Wm = (torch.randn(10240, 1280, device="cuda") * 0.03).to(torch.bfloat16)
+    g = torch.rand(10240, device="cuda") + 0.5
+    dW = torch.randn(10240, 1280, device="cuda")
+    w1 = torch.randn(8, 8, device="cuda") * 0.3
+    w2 = torch.randn(1280, 160, device="cuda") * 0.02
+    d = k.make_desc(k.ALGO_LOKR, 10240, 1280, factors=[w1, w2], w_dtype=torch.float32, up=8, uq=8, vp=1280, vq=160)
+    for _ in range(reps):
+        out, sumsq = k.dora_fwd(Wm, g, True, 1, 1.0, 1.19e-7)
+        k.dora_bwd(dW, Wm, g, sumsq, True, 1, 1.0, 1.19e-7)
+        k.delta_weight(d, (10240, 1280), torch.float32, None, True, True)
     torch.cuda.synchronize()
     print("ncu layout target done")
 
