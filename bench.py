@@ -347,6 +347,8 @@ def run_engine(args):
 
     def capture(fn):
         try:
+            torch.cuda.synchronize()
+            torch.cuda.empty_cache()  # the eager warm-up's cached blocks: the graph gets its own pool (cfg5: batch 16)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 out = fn()
@@ -581,7 +583,9 @@ def run_engine(args):
     if world == 1 and not args.skip_gpu_reference:
         del graph
         graph = None
+        static_loss = None
         torch.cuda.synchronize()
+        torch.cuda.empty_cache()
         result["gpu_eager_reference"] = gpu_eager_reference(args, unet, net, static, loss_val)
         ref = result["gpu_eager_reference"]
         if ref.get("ms_per_step"):
