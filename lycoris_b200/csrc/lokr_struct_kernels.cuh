@@ -132,27 +132,27 @@ __global__ void __launch_bounds__(256) lokr_w1grad_kernel(const uint16_t* __rest
     const int c8 = static_cast<int>(idx - m * nc8);
     const uint4* pp = reinterpret_cast<const uint4*>(P) + (m * na) * nc8 + c8;
     const uint4* rp = reinterpret_cast<const uint4*>(R) + (m * nb) * nc8 + c8;
+    // all NA + NB vectors of this (m, c8) are requested before any is consumed: 16 x 16 bytes in flight per thread is
+    // what hides the DRAM latency at one resident CTA per SM (round-2 profile: with the P loads issued one per
+    // a-iteration the kernel ran at 0.78 TB/s, latency-bound)
+    uint4 rraw[NB], praw[NA];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) rraw[b] = b < nb ? __ldg(rp + static_cast<int64_t>(b) * nc8) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int a = 0; a < NA; ++a) praw[a] = a < na ? __ldg(pp + static_cast<int64_t>(a) * nc8) : make_uint4(0, 0, 0, 0);
     float r[NB][8];
 #pragma unroll
-    for (int b = 0; b < NB; ++b) {
-      if (b < nb) unpack8(__ldg(rp + static_cast<int64_t>(b) * nc8), r[b], fmt);
-      else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) r[b][j] = 0.f;
-      }
-    }
+    for (int b = 0; b < NB; ++b) unpack8(rraw[b], r[b], fmt);
 #pragma unroll
     for (int a = 0; a < NA; ++a) {
-      if (a < na) {
-        float p[8];
-        unpack8(__ldg(pp + static_cast<int64_t>(a) * nc8), p, fmt);
+      float p[8];
+      unpack8(praw[a], p, fmt);
 #pragma unroll
-        for (int b = 0; b < NB; ++b) {
-          float s = acc[a][b];
+      for (int b = 0; b < NB; ++b) {
+        float s = acc[a][b];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) s = fmaf(p[j], r[b][j], s);
-          acc[a][b] = s;
-        }
+        for (int j = 0; j < 8; ++j) s = fmaf(p[j], r[b][j], s);
+        acc[a][b] = s;
       }
     }
   }

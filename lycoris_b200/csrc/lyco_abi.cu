@@ -943,7 +943,8 @@ int lyco_lokr_w1grad(const void* P, const void* R, float* g_w1, int64_t M, int n
   const int nc8 = nc / 8;
   const int64_t work = M * nc8;
   int64_t grid = (work + 255) / 256;
-  const int64_t cap = static_cast<int64_t>(di.sms) * 4;  // few, long-lived CTAs: the final reduction is per CTA
+  const int64_t cap = di.sms;  // one resident CTA per SM (150 registers per thread), each thread loops over its items:
+                               // the butterfly + 64 global atomics per CTA are paid once per SM, not once per wave
   if (grid > cap) grid = cap;
   const int fmt = dtype == LYCO_BF16 ? 1 : 0;
   const uint16_t* p = static_cast<const uint16_t*>(P);
