@@ -247,8 +247,10 @@ def _lowrank_operands(spec, factors, prod):
     return [o.contiguous() for o in ops]
 
 
-def _lowrank_merge(spec, factors, W, prod, out_dim, in_dim):
+def _lowrank_merge(spec, factors, W, prod, out_dim, in_dim, keep=None):
     f = _lowrank_operands(spec, factors, prod)
+    if keep is not None:
+        keep.extend(f)  # the 16-bit operand copies are reused by backward (4 cast kernels less per LoHa layer-step)
     raws = [K.gemm(f[0], f[1], b_mn=True)]  # [N, r] x [r, K'] -> [N, K'], rounded to `prod` like the reference's matmul
     if spec.algo == K.ALGO_LOHA:
         raws.append(K.gemm(f[2], f[3], b_mn=True))
@@ -257,15 +259,31 @@ def _lowrank_merge(spec, factors, W, prod, out_dim, in_dim):
     return K.merge_weight(desc, W)
 
 
-def _lowrank_grads(spec, factors, dWm, prod):
+def _zeroed_views(shapes, device):
+    """fp32 tensors of ``shapes`` carved out of ONE zero-filled buffer (64-float aligned): the split-K contractions
+    that follow ADD into them (accumulate mode), so a layer pays one fill instead of one memset per gradient."""
+    sizes = [int(torch.Size(s).numel()) for s in shapes]
+    offs, total = [], 0
+    for n in sizes:
+        offs.append(total)
+        total += (n + 63) // 64 * 64
+    flat = torch.zeros(total, device=device, dtype=torch.float32)
+    return [flat[o:o + n].view(s) for o, n, s in zip(offs, sizes, shapes)]
+
+
+def _lowrank_grads(spec, factors, dWm, prod, f=None):
     """Factor gradients from fp32 dW' with skinny tensor-core contractions (fp32 outputs)."""
-    f = _lowrank_operands(spec, factors, prod)
+    if not f:
+        f = _lowrank_operands(spec, factors, prod)
     gscale = spec.m_pre * spec.m_post1 * spec.m_post2
     f32 = torch.float32
+    N, r = f[0].shape
+    Kp = f[1].shape[1]
     if spec.algo != K.ALGO_LOHA:
         G = K.grad_prep(dWm, None, gscale, prod)
-        g_up = K.gemm(G, f[1], out_dtype=f32)                          # G · downᵀ          [N, r]
-        g_down = K.gemm(f[0], G, a_mn=True, b_mn=True, out_dtype=f32)  # upᵀ · G            [r, K']
+        g_up, g_down = _zeroed_views([(N, r), (r, Kp)], dWm.device)
+        K.gemm(G, f[1], out=g_up, out_dtype=f32, accumulate=True)                          # G · downᵀ    [N, r]
+        K.gemm(f[0], G, a_mn=True, b_mn=True, out=g_down, out_dtype=f32, accumulate=True)  # upᵀ · G      [r, K']
         if spec.algo == K.ALGO_DYLORA and spec.m_in != 1.0:
             g_down = g_down * spec.m_in
         return [g_up, g_down]
@@ -273,8 +291,12 @@ def _lowrank_grads(spec, factors, dWm, prod):
     P2 = K.gemm(f[2], f[3], b_mn=True)
     G1 = K.grad_prep(dWm, P2, gscale, prod)
     G2 = K.grad_prep(dWm, P1, gscale, prod)
-    return [K.gemm(G1, f[1], out_dtype=f32), K.gemm(f[0], G1, a_mn=True, b_mn=True, out_dtype=f32),
-            K.gemm(G2, f[3], out_dtype=f32), K.gemm(f[2], G2, a_mn=True, b_mn=True, out_dtype=f32)]
+    g = _zeroed_views([(N, r), (r, Kp), (N, r), (r, Kp)], dWm.device)
+    K.gemm(G1, f[1], out=g[0], out_dtype=f32, accumulate=True)
+    K.gemm(f[0], G1, a_mn=True, b_mn=True, out=g[1], out_dtype=f32, accumulate=True)
+    K.gemm(G2, f[3], out=g[2], out_dtype=f32, accumulate=True)
+    K.gemm(f[2], G2, a_mn=True, b_mn=True, out=g[3], out_dtype=f32, accumulate=True)
+    return g
 
 
 # ------------------------------------------------------- LoCon / DyLoRA side path (no merged weight)
@@ -326,15 +348,17 @@ class _LoconSidePath(torch.autograd.Function):
         U = K.gemm(dy2, up_s, b_mn=True) if (need_x or need_down) else None  # [M, r] = dY·(s·up)
         if need_x:
             dx = K.gemm_dual(dy2, W, U, down_c, b_mn=True).view(x.shape)     # dY·W + U·down
+        r = T.shape[1]
+        zu, zd = _zeroed_views([(N, r), (r, W.shape[1])], dy2.device) if (need_up or need_down) else (None, None)
         if need_up:
-            g_up = K.gemm(dy2, T, a_mn=True, b_mn=True, out_dtype=f32)       # dYᵀ·T   [N, r]
+            g_up = K.gemm(dy2, T, a_mn=True, b_mn=True, out=zu, out_dtype=f32, accumulate=True)   # dYᵀ·T   [N, r]
             if ctx.scale != 1.0:
                 g_up = g_up * ctx.scale
         if need_down:
             x2 = x.reshape(-1, x.shape[-1])
             if not x2.is_contiguous():
                 x2 = x2.contiguous()
-            g_down = K.gemm(U, x2, a_mn=True, b_mn=True, out_dtype=f32)      # Uᵀ·X    [r, K]
+            g_down = K.gemm(U, x2, a_mn=True, b_mn=True, out=zd, out_dtype=f32, accumulate=True)  # Uᵀ·X    [r, K]
             if spec.algo == K.ALGO_DYLORA and spec.m_in != 1.0:
                 g_down = g_down * spec.m_in
         if g_up is not None and g_up.dtype != ctx.f_dtypes[0]:
@@ -408,10 +432,10 @@ class _AdapterContraction(torch.autograd.Function):
     """y = op(x, merge(W, factors), bias) with everything on the sm_100a kernels."""
 
     @staticmethod
-    def _merge(spec, factors_u, W, ac_dtype, out_dim, in_dim):
+    def _merge(spec, factors_u, W, ac_dtype, out_dim, in_dim, keep=None):
         prod = _lowrank_tc_dtype(spec, factors_u, out_dim, in_dim, ac_dtype)
         if prod is not None:
-            return _lowrank_merge(spec, factors_u, W, prod, out_dim, in_dim)
+            return _lowrank_merge(spec, factors_u, W, prod, out_dim, in_dim, keep)
         return K.merge_weight(_build_desc(spec, factors_u, W.dtype, ac_dtype, out_dim, in_dim), W)
 
     @staticmethod
@@ -429,7 +453,8 @@ class _AdapterContraction(torch.autograd.Function):
         factors_u = _uniform_factors(factors)
         out_dim = W.shape[0]
         in_dim = W.numel() // out_dim
-        Wm = _AdapterContraction._merge(spec, factors_u, W, ac_dtype, out_dim, in_dim)
+        ctx.lowrank_ops = []
+        Wm = _AdapterContraction._merge(spec, factors_u, W, ac_dtype, out_dim, in_dim, ctx.lowrank_ops)
         sumsq = None
         if spec.dora is not None:
             g32, on_out, taps, mult, eps, sdt = _AdapterContraction._dora_args(spec, W)
@@ -494,7 +519,7 @@ class _AdapterContraction(torch.autograd.Function):
                         g_dora = g_dora.view(ds.shape).to(ds.dtype)
                 prod = _lowrank_tc_dtype(spec, factors_u, out_dim, in_dim, ctx.ac_dtype)
                 if prod is not None:
-                    gs = _lowrank_grads(spec, factors_u, dWm, prod)
+                    gs = _lowrank_grads(spec, factors_u, dWm, prod, ctx.lowrank_ops)
                 else:
                     desc = _build_desc(spec, factors_u, W.dtype, ctx.ac_dtype, out_dim, in_dim)
                     gs = K.factor_grads(desc, dWm, W, [f.shape for f in factors_u])
