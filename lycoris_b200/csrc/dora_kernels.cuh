@@ -8,6 +8,7 @@
 #include <stdint.h>
 
 #include "weight_kernels.cuh"
+#include "lokr_struct_kernels.cuh"  // unpack8 / pack8
 
 namespace lyco {
 
@@ -98,6 +99,154 @@ __global__ void __launch_bounds__(256) dora_apply_bwd_kernel(float* __restrict__
     const float s = dora_scale_of(ss, gg, mult, eps, sdt);
     const float b = nrm > 0.f ? mult * gg * tt / (ne * ne * nrm) : 0.f;
     dW[idx] = s * dW[idx] - b * cvt16(Wm[idx], w_dtype);
+  }
+}
+
+// ---- vector variants (K % 8 == 0, 16-byte aligned arrays): one warp walks one weight row, lanes stride over its
+// 16-byte vectors — the (n, k) decomposition costs nothing, loads and stores are 16 bytes wide, row groups need no
+// atomics at all.  The scalar kernels above remain for ragged shapes.
+
+// row groups (on_out = 1): acc[n] = sum_k a*b, written directly (no memset, no atomics)
+template <int MODE>
+__global__ void __launch_bounds__(256) dora_reduce_rows_vec_kernel(const float* __restrict__ A, const uint16_t* __restrict__ Wm,
+                                                                   float* __restrict__ acc, int N, int K, int w_dtype) {
+  const int kv = K >> 3, lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int fmt = w_dtype == LYCO_BF16 ? 1 : 0;
+  for (int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; n < N; n += warps) {
+    const uint4* wrow = reinterpret_cast<const uint4*>(Wm + static_cast<int64_t>(n) * K);
+    const float4* arow = MODE == 1 ? reinterpret_cast<const float4*>(A + static_cast<int64_t>(n) * K) : nullptr;
+    float s = 0.f;
+    for (int i = lane; i < kv; i += 32) {
+      float w[8];
+      unpack8(__ldg(wrow + i), w, fmt);
+      if (MODE == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s = fmaf(w[j], w[j], s);
+      } else {
+        const float4 a0 = __ldg(arow + 2 * i), a1 = __ldg(arow + 2 * i + 1);
+        s = fmaf(a0.x, w[0], s); s = fmaf(a0.y, w[1], s); s = fmaf(a0.z, w[2], s); s = fmaf(a0.w, w[3], s);
+        s = fmaf(a1.x, w[4], s); s = fmaf(a1.y, w[5], s); s = fmaf(a1.z, w[6], s); s = fmaf(a1.w, w[7], s);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) acc[n] = s;
+  }
+}
+
+// column groups (on_out = 0): a thread owns one 8-column vector over a strip of 32 rows; acc must be zero-filled
+template <int MODE>
+__global__ void __launch_bounds__(256) dora_reduce_cols_vec_kernel(const float* __restrict__ A, const uint16_t* __restrict__ Wm,
+                                                                   float* __restrict__ acc, int N, int K, int taps,
+                                                                   int w_dtype) {
+  const int kv = K >> 3;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kv) return;
+  const int n0 = blockIdx.y * 32, n1 = min(N, n0 + 32);
+  const int fmt = w_dtype == LYCO_BF16 ? 1 : 0;
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int n = n0; n < n1; ++n) {
+    float w[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(Wm + static_cast<int64_t>(n) * K) + i), w, fmt);
+    if (MODE == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] = fmaf(w[j], w[j], s[j]);
+    } else {
+      const float4* ar = reinterpret_cast<const float4*>(A + static_cast<int64_t>(n) * K) + 2 * i;
+      const float4 a0 = __ldg(ar), a1 = __ldg(ar + 1);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] = fmaf(a[j], w[j], s[j]);
+    }
+  }
+  // neighbouring columns of one input channel (taps > 1) are folded before the atomic
+  int g_prev = (8 * i) / taps;
+  float run = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int gj = (8 * i + j) / taps;
+    if (gj != g_prev) {
+      atomicAdd(&acc[g_prev], run);
+      run = 0.f;
+      g_prev = gj;
+    }
+    run += s[j];
+  }
+  atomicAdd(&acc[g_prev], run);
+}
+
+// forward apply, vectorised: W''[n, k..k+7] = rnd16(rnd_s(Wm * s[group]))
+__global__ void __launch_bounds__(256) dora_apply_fwd_vec_kernel(const uint16_t* __restrict__ Wm, uint16_t* __restrict__ Wout,
+                                                                 const float* __restrict__ sumsq, const float* __restrict__ g,
+                                                                 int N, int K, int on_out, int taps, float mult, float eps,
+                                                                 int w_dtype, int sdt) {
+  const int kv = K >> 3, lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int fmt = w_dtype == LYCO_BF16 ? 1 : 0;
+  for (int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; n < N; n += warps) {
+    const uint4* wrow = reinterpret_cast<const uint4*>(Wm + static_cast<int64_t>(n) * K);
+    uint4* orow = reinterpret_cast<uint4*>(Wout + static_cast<int64_t>(n) * K);
+    const float s_row = on_out ? dora_scale_of(__ldg(sumsq + n), __ldg(g + n), mult, eps, sdt) : 0.f;
+    for (int i = lane; i < kv; i += 32) {
+      float w[8], o[8];
+      unpack8(__ldg(wrow + i), w, fmt);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float sc = s_row;
+        if (!on_out) {
+          const int grp = (8 * i + j) / taps;
+          sc = dora_scale_of(__ldg(sumsq + grp), __ldg(g + grp), mult, eps, sdt);
+        }
+        o[j] = rnd(w[j] * sc, sdt);
+      }
+      orow[i] = pack8(o, fmt);
+    }
+  }
+}
+
+// backward apply, vectorised and in place over the fp32 dW; g_scale written by the first `groups` threads
+__global__ void __launch_bounds__(256) dora_apply_bwd_vec_kernel(float* __restrict__ dW, const uint16_t* __restrict__ Wm,
+                                                                 const float* __restrict__ sumsq, const float* __restrict__ g,
+                                                                 const float* __restrict__ t, float* __restrict__ dg, int N,
+                                                                 int K, int on_out, int taps, float mult, float eps,
+                                                                 int w_dtype, int groups, int sdt) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int q = tid; dg != nullptr && q < groups; q += gridDim.x * blockDim.x)
+    dg[q] = __ldg(t + q) * mult / (sqrtf(__ldg(sumsq + q)) + eps);
+  const int kv = K >> 3, lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int fmt = w_dtype == LYCO_BF16 ? 1 : 0;
+  for (int n = tid >> 5; n < N; n += warps) {
+    const uint4* wrow = reinterpret_cast<const uint4*>(Wm + static_cast<int64_t>(n) * K);
+    float4* drow = reinterpret_cast<float4*>(dW + static_cast<int64_t>(n) * K);
+    float a_row = 0.f, b_row = 0.f;
+    if (on_out) {
+      const float ss = __ldg(sumsq + n), gg = __ldg(g + n), tt = __ldg(t + n);
+      const float nrm = sqrtf(ss), ne = nrm + eps;
+      a_row = dora_scale_of(ss, gg, mult, eps, sdt);
+      b_row = nrm > 0.f ? mult * gg * tt / (ne * ne * nrm) : 0.f;
+    }
+    for (int i = lane; i < kv; i += 32) {
+      float w[8];
+      unpack8(__ldg(wrow + i), w, fmt);
+      float4 d0 = drow[2 * i], d1 = drow[2 * i + 1];
+      float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float a = a_row, b = b_row;
+        if (!on_out) {
+          const int grp = (8 * i + j) / taps;
+          const float ss = __ldg(sumsq + grp), gg = __ldg(g + grp), tt = __ldg(t + grp);
+          const float nrm = sqrtf(ss), ne = nrm + eps;
+          a = dora_scale_of(ss, gg, mult, eps, sdt);
+          b = nrm > 0.f ? mult * gg * tt / (ne * ne * nrm) : 0.f;
+        }
+        d[j] = a * d[j] - b * w[j];
+      }
+      drow[2 * i] = make_float4(d[0], d[1], d[2], d[3]);
+      drow[2 * i + 1] = make_float4(d[4], d[5], d[6], d[7]);
+    }
   }
 }
 

@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 
 #include "../../include/lyco_b200.h"
@@ -995,16 +996,30 @@ int lyco_dora_fwd(const void* Wm, void* W_out, const float* dora_scale, float* s
   DeviceInfo di;
   if (device_info(&di)) return 1;
   const int groups = on_out ? N : K / taps;
-  LYCO_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(float) * groups, stream));
-  const dim3 rgrid(cdiv(K, 256), cdiv(N, 64));
   const uint16_t* wm = static_cast<const uint16_t*>(Wm);
-  lyco::dora_reduce_kernel<0><<<rgrid, 256, 0, stream>>>(nullptr, wm, sumsq, N, K, on_out, taps, w_dtype);
   const int64_t total = static_cast<int64_t>(N) * K;
-  int64_t grid = (total + 255) / 256;
   const int64_t cap = static_cast<int64_t>(di.sms) * 16;
-  if (grid > cap) grid = cap;
-  lyco::dora_apply_fwd_kernel<<<static_cast<int>(grid), 256, 0, stream>>>(wm, static_cast<uint16_t*>(W_out), sumsq, dora_scale,
-                                                                         N, K, on_out, taps, mult, eps, w_dtype, scale_dtype);
+  const bool vec = K % 8 == 0 && ((reinterpret_cast<uintptr_t>(Wm) | reinterpret_cast<uintptr_t>(W_out)) & 15) == 0;
+  if (vec) {
+    int wgrid = static_cast<int>(std::min<int64_t>(cap, cdiv(N, 8)));  // 8 warps = 8 rows per CTA
+    if (on_out) {
+      lyco::dora_reduce_rows_vec_kernel<0><<<wgrid, 256, 0, stream>>>(nullptr, wm, sumsq, N, K, w_dtype);
+    } else {
+      LYCO_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(float) * groups, stream));
+      const dim3 cgrid(cdiv(K / 8, 256), cdiv(N, 32));
+      lyco::dora_reduce_cols_vec_kernel<0><<<cgrid, 256, 0, stream>>>(nullptr, wm, sumsq, N, K, taps, w_dtype);
+    }
+    lyco::dora_apply_fwd_vec_kernel<<<wgrid, 256, 0, stream>>>(wm, static_cast<uint16_t*>(W_out), sumsq, dora_scale, N, K,
+                                                               on_out, taps, mult, eps, w_dtype, scale_dtype);
+  } else {
+    LYCO_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(float) * groups, stream));
+    const dim3 rgrid(cdiv(K, 256), cdiv(N, 64));
+    lyco::dora_reduce_kernel<0><<<rgrid, 256, 0, stream>>>(nullptr, wm, sumsq, N, K, on_out, taps, w_dtype);
+    int64_t grid = (total + 255) / 256;
+    if (grid > cap) grid = cap;
+    lyco::dora_apply_fwd_kernel<<<static_cast<int>(grid), 256, 0, stream>>>(wm, static_cast<uint16_t*>(W_out), sumsq, dora_scale,
+                                                                           N, K, on_out, taps, mult, eps, w_dtype, scale_dtype);
+  }
   LYCO_CUDA(cudaGetLastError());
   g_launches.fetch_add(2, std::memory_order_relaxed);
   return 0;
@@ -1019,17 +1034,31 @@ int lyco_dora_bwd(float* dW, const void* Wm, const float* dora_scale, const floa
   DeviceInfo di;
   if (device_info(&di)) return 1;
   const int groups = on_out ? N : K / taps;
-  LYCO_CUDA(cudaMemsetAsync(t, 0, sizeof(float) * groups, stream));
-  const dim3 rgrid(cdiv(K, 256), cdiv(N, 64));
   const uint16_t* wm = static_cast<const uint16_t*>(Wm);
-  lyco::dora_reduce_kernel<1><<<rgrid, 256, 0, stream>>>(dW, wm, t, N, K, on_out, taps, w_dtype);
   const int64_t total = static_cast<int64_t>(N) * K;
-  int64_t grid = (total + 255) / 256;
   const int64_t cap = static_cast<int64_t>(di.sms) * 16;
-  if (grid > cap) grid = cap;
-  if (grid * 256 < groups) grid = (groups + 255) / 256;  // the first `groups` threads also write g_scale
-  lyco::dora_apply_bwd_kernel<<<static_cast<int>(grid), 256, 0, stream>>>(dW, wm, sumsq, dora_scale, t, g_scale, N, K, on_out,
-                                                                         taps, mult, eps, w_dtype, groups, scale_dtype);
+  const bool vec = K % 8 == 0 && ((reinterpret_cast<uintptr_t>(Wm) | reinterpret_cast<uintptr_t>(dW)) & 15) == 0;
+  if (vec) {
+    int wgrid = static_cast<int>(std::min<int64_t>(cap, cdiv(N, 8)));
+    if (on_out) {
+      lyco::dora_reduce_rows_vec_kernel<1><<<wgrid, 256, 0, stream>>>(dW, wm, t, N, K, w_dtype);
+    } else {
+      LYCO_CUDA(cudaMemsetAsync(t, 0, sizeof(float) * groups, stream));
+      const dim3 cgrid(cdiv(K / 8, 256), cdiv(N, 32));
+      lyco::dora_reduce_cols_vec_kernel<1><<<cgrid, 256, 0, stream>>>(dW, wm, t, N, K, taps, w_dtype);
+    }
+    lyco::dora_apply_bwd_vec_kernel<<<wgrid, 256, 0, stream>>>(dW, wm, sumsq, dora_scale, t, g_scale, N, K, on_out, taps, mult,
+                                                               eps, w_dtype, groups, scale_dtype);
+  } else {
+    LYCO_CUDA(cudaMemsetAsync(t, 0, sizeof(float) * groups, stream));
+    const dim3 rgrid(cdiv(K, 256), cdiv(N, 64));
+    lyco::dora_reduce_kernel<1><<<rgrid, 256, 0, stream>>>(dW, wm, t, N, K, on_out, taps, w_dtype);
+    int64_t grid = (total + 255) / 256;
+    if (grid > cap) grid = cap;
+    if (grid * 256 < groups) grid = (groups + 255) / 256;  // the first `groups` threads also write g_scale
+    lyco::dora_apply_bwd_kernel<<<static_cast<int>(grid), 256, 0, stream>>>(dW, wm, sumsq, dora_scale, t, g_scale, N, K, on_out,
+                                                                           taps, mult, eps, w_dtype, groups, scale_dtype);
+  }
   LYCO_CUDA(cudaGetLastError());
   g_launches.fetch_add(2, std::memory_order_relaxed);
   return 0;
