@@ -368,6 +368,46 @@ class _LoconSidePath(torch.autograd.Function):
         return dx, None, None, None, g_up, g_down
 
 
+def _locon_conv_skinny_ok(spec, conv, info, w):
+    """LoCon / DyLoRA on an engine-run k x k convolution: factor gradients without the dense dW' (see below)."""
+    return (_LOCON_SIDE and conv is not None and spec.algo in (K.ALGO_LOCON, K.ALGO_DYLORA) and spec.dora is None
+            and info[0] and w.dim() == 4 and spec.rank % 8 == 0 and 8 <= spec.rank <= 256
+            and w.shape[2] * w.shape[3] <= 9 and w.shape[1] % 64 == 0 and w.shape[0] % 8 == 0)
+
+
+def _locon_conv_skinny_grads(spec, factors, dy, xs, w_shape, conv):
+    """[g_up, g_down] (fp32) of a LoCon / DyLoRA convolution from two skinny convolutions and two skinny GEMMs — the
+    bypass-order contraction (lora_down k x k conv, then lora_up 1 x 1; locon.py:273-307) applied to the GRADIENTS:
+        T = conv(X, down)  [pixels, r]        U = dY . (s up)  [pixels, r]
+        g_up = s . dY^T T  [O, r]             g_down = wgrad(X, U)  [r, C k k]
+    instead of the dense dW' = wgrad(X, dY) [O, C k k] + one reduction pass over it: 2 r / O of the dense FLOPs."""
+    O, C, R, S = w_shape
+    up, down = factors                      # [O, r], [r, C*R*S]
+    r = up.shape[1]
+    cdt = xs.dtype
+    s_ = spec.m_pre * spec.m_post1 * spec.m_post2
+    down_c = (down * spec.m_in if (spec.algo == K.ALGO_DYLORA and spec.m_in != 1.0) else down).to(cdt)
+    up_s = (up * s_ if s_ != 1.0 else up).to(cdt).contiguous()
+    st, pad = conv["stride"][0], conv["padding"]
+    down_k = K.filter_relayout(down_c.reshape(r, C, R, S).contiguous(), K.FILTER_FPROP)       # [r, R*S*C]
+    T = K.conv2d_fprop(xs, down_k, None, R, S, pad, st)                                       # NHWC [Nb, r, P, Q]
+    dyc = K.as_nhwc(dy, cdt)
+    Nb, _, P, Q = dyc.shape
+    dY2 = dyc.permute(0, 2, 3, 1).reshape(Nb * P * Q, O)
+    T2 = T.permute(0, 2, 3, 1).reshape(Nb * P * Q, r)
+    U2 = K.gemm(dY2, up_s, b_mn=True)                                                        # [pixels, r]
+    g_up, = _zeroed_views([(O, r)], dy.device)
+    K.gemm(dY2, T2, a_mn=True, b_mn=True, out=g_up, out_dtype=torch.float32, accumulate=True)
+    if s_ != 1.0:
+        g_up = g_up * s_
+    U4 = U2.view(Nb, P, Q, r).permute(0, 3, 1, 2)                                            # NHWC storage
+    g_down_k = K.conv2d_wgrad(xs, U4, R, S, pad, st)                                         # [r, R*S*C] fp32
+    g_down = K.filter_relayout((g_down_k, (r, C, R, S)), K.FILTER_WBACK).reshape(r, C * R * S)
+    if spec.algo == K.ALGO_DYLORA and spec.m_in != 1.0:
+        g_down = g_down * spec.m_in
+    return [g_up, g_down]
+
+
 # ------------------------------------------------------- structured LoKr factor gradients
 # dW = kron(w1, w2): g_w1 / g_w2 from two skinny contractions (1/uq of the dense FLOPs each) instead of the dense
 # fp32 dW' = dYᵀ·X + a reduction pass over it (lokr_struct_kernels.cuh).  The structured form trades FLOPs for HBM
@@ -498,6 +538,9 @@ class _AdapterContraction(torch.autograd.Function):
                     gs = _lokr_structured_grads(spec, _uniform_factors(factors), dy2, x2)
                 else:
                     dWm = _dense_tn_f32(dy2, x2)
+        elif need_f and _locon_conv_skinny_ok(spec, conv, ctx.conv_info, Wm):
+            dx, _ = _conv_backward(dy, x, Wm, conv, ctx.conv_info, need_x, False)
+            gs = _locon_conv_skinny_grads(spec, _uniform_factors(factors), dy, x, Wm.shape, conv)
         else:
             dx, dw = _conv_backward(dy, x, Wm, conv, ctx.conv_info, need_x, need_f)
             if need_f:

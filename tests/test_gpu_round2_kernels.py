@@ -229,6 +229,50 @@ def test_locon_side_path_matches_merged_path_and_fp64(algo, M, N, K, r):
         assert rel_err(gs[k_], gm[k_]) <= 3e-2, (k_, rel_err(gs[k_], gm[k_]))
 
 
+@pytest.mark.parametrize("C,O,k,stride,side,r", [(64, 128, 3, 1, 16, 8), (64, 64, 3, 2, 16, 8), (320, 320, 3, 1, 64, 8),
+                                                 (128, 64, 1, 1, 16, 16), (1280, 1280, 3, 1, 32, 8)])
+def test_locon_conv_skinny_factor_gradients_match_dense_path(C, O, k, stride, side, r):
+    """LoCon on an engine-run convolution: g_up / g_down from T = conv(X, down), U = dY.(s up), dY^T T and wgrad(X, U)
+    (no dense dW' = wgrad(X, dY)) against the merged-weight path's dense dW' + reduction on the same layer."""
+    import lycoris_b200 as L
+    from lycoris_b200.engine import ops
+
+    torch.manual_seed(0)
+    base = nn.Conv2d(C, O, k, stride, k // 2).cuda().to(torch.bfloat16)
+    base.requires_grad_(False)
+    mod = L.LoConModule("t", base, 0.7, r, r / 2).cuda()
+    with torch.no_grad():
+        mod.lora_up.weight.normal_(0, 0.05)
+    gen = torch.Generator().manual_seed(3)
+    x = torch.randn(2, C, side, side, generator=gen).cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    mod.apply_to()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        yshape = base(x).shape
+    dy = (torch.randn(yshape, generator=gen) * 0.1).cuda().to(torch.bfloat16)
+
+    def run(side_path):
+        saved = ops._LOCON_SIDE
+        ops._LOCON_SIDE = side_path
+        try:
+            for p in mod.parameters():
+                p.grad = None
+            xe = x.clone().requires_grad_(True)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                y = base(xe)
+            y.backward(dy)
+            return y.detach(), xe.grad, mod.lora_up.weight.grad.clone(), mod.lora_down.weight.grad.clone()
+        finally:
+            ops._LOCON_SIDE = saved
+
+    ys, dxs, gus, gds = run(True)
+    yd, dxd, gud, gdd = run(False)
+    mod.restore()
+    assert torch.equal(ys, yd) and torch.equal(dxs, dxd)  # forward and dX still use the merged weight
+    assert gus.shape == gud.shape and gds.shape == gdd.shape
+    assert rel_err(gus, gud) <= 2e-2, ("up", rel_err(gus, gud))
+    assert rel_err(gds, gdd) <= 2e-2, ("down", rel_err(gds, gdd))
+
+
 # ------------------------------------------------------------------------------------------ delta weight
 def _mods(dtype):
     import lycoris_b200 as L
