@@ -502,8 +502,8 @@ def run_engine(args):
     achieved_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        graph = static_loss = step = one_step = None  # drop the captured graphs (they pin the NCCL communicator)
+        shutdown_process_group(world)
         return
     steps_per_s = world * 1000.0 / ms_step
     traffic = ncu_traffic(wl["name"])
@@ -596,8 +596,8 @@ def run_engine(args):
     if not args.skip_cpu_baseline and world == 1:
         result["cpu_baseline"] = cpu_reference(args, budget_s=args.cpu_seconds, reps=3)
     print(json.dumps(result), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    graph = static_loss = step = one_step = None
+    shutdown_process_group(world)
     ref = result.get("gpu_eager_reference") or {}
     if ref.get("loss_check") == "FAILED":
         # the line above is still printed (with loss_check = FAILED); a parity failure at the headline config must not
@@ -605,6 +605,31 @@ def run_engine(args):
         print(f"[bench] PARITY FAILURE: engine loss {ref['engine_loss']} vs reference loss {ref['loss']} "
               f"(relative difference {ref['loss_rel_diff']:.3e} > 2e-2)", file=sys.stderr)
         sys.exit(3)
+
+
+def shutdown_process_group(world):
+    """Leave the NCCL group without hanging: ncclCommDestroy waits for every CUDA graph that captured the communicator
+    (the step graph holds the bucketed all-reduces), so the graphs must be gone first; a watchdog ends the process if
+    the teardown still blocks (the JSON line is already printed and flushed by then)."""
+    if world <= 1:
+        return
+    import gc
+
+    import torch
+    import torch.distributed as dist
+
+    gc.collect()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    dog = threading.Timer(20.0, lambda: os._exit(0))
+    dog.daemon = True
+    dog.start()
+    try:
+        dist.destroy_process_group()
+    except Exception:  # noqa: BLE001
+        pass
+    dog.cancel()
 
 
 def profile_one_step(args, step):
