@@ -109,7 +109,8 @@ __global__ void __launch_bounds__(256) dora_apply_bwd_kernel(float* __restrict__
 // row groups (on_out = 1): acc[n] = sum_k a*b, written directly (no memset, no atomics)
 template <int MODE>
 __global__ void __launch_bounds__(256) dora_reduce_rows_vec_kernel(const float* __restrict__ A, const uint16_t* __restrict__ Wm,
-                                                                   float* __restrict__ acc, int N, int K, int w_dtype) {
+                                                                   float* __restrict__ acc, int N, int K, int w_dtype,
+                                                                   float scale = 1.f) {
   const int kv = K >> 3, lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   const int fmt = w_dtype == LYCO_BF16 ? 1 : 0;
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(256) dora_reduce_rows_vec_kernel(const float* 
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) acc[n] = s;
+    if (lane == 0) acc[n] = s * scale;
   }
 }
 
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(256) dora_reduce_rows_vec_kernel(const float* 
 template <int MODE>
 __global__ void __launch_bounds__(256) dora_reduce_cols_vec_kernel(const float* __restrict__ A, const uint16_t* __restrict__ Wm,
                                                                    float* __restrict__ acc, int N, int K, int taps,
-                                                                   int w_dtype) {
+                                                                   int w_dtype, float scale = 1.f) {
   const int kv = K >> 3;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= kv) return;
@@ -167,13 +168,41 @@ __global__ void __launch_bounds__(256) dora_reduce_cols_vec_kernel(const float* 
   for (int j = 0; j < 8; ++j) {
     const int gj = (8 * i + j) / taps;
     if (gj != g_prev) {
-      atomicAdd(&acc[g_prev], run);
+      atomicAdd(&acc[g_prev], run * scale);
       run = 0.f;
       g_prev = gj;
     }
     run += s[j];
   }
-  atomicAdd(&acc[g_prev], run);
+  atomicAdd(&acc[g_prev], run * scale);
+}
+
+// (IA)^3 merge, vectorised: W'[n, k..k+7] = rnd_w(rnd_cd(W * (1 + w[group] * mult)))  (ia3.py:91-102), warp per row
+__global__ void __launch_bounds__(256) merge_ia3_vec_kernel(lyco_delta_desc_t d, const uint16_t* __restrict__ W,
+                                                            uint16_t* __restrict__ Wout) {
+  const int K = d.in_dim, N = d.out_dim;
+  const int kv = K >> 3, lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int cd = d.f_dtype;  // dtype the scale is computed in (fp32: no rounding)
+  const int pd = cd == LYCO_F32 ? LYCO_F32 : d.w_dtype;
+  const int fmt = d.w_dtype == LYCO_BF16 ? 1 : 0;
+  for (int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; n < N; n += warps) {
+    const uint4* wrow = reinterpret_cast<const uint4*>(W + static_cast<int64_t>(n) * K);
+    uint4* orow = reinterpret_cast<uint4*>(Wout + static_cast<int64_t>(n) * K);
+    float s_row = 0.f;
+    if (!d.on_input) s_row = rnd(rnd(ld_f(d.f0, d.f_dtype, n) * d.m_post2, cd) + 1.f, cd);
+    for (int i = lane; i < kv; i += 32) {
+      float w[8], o[8];
+      unpack8(__ldg(wrow + i), w, fmt);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float sc = s_row;
+        if (d.on_input) sc = rnd(rnd(ld_f(d.f0, d.f_dtype, (8 * i + j) / d.ia3_group) * d.m_post2, cd) + 1.f, cd);
+        o[j] = rnd(w[j] * sc, pd);
+      }
+      orow[i] = pack8(o, fmt);
+    }
+  }
 }
 
 // forward apply, vectorised: W''[n, k..k+7] = rnd16(rnd_s(Wm * s[group]))

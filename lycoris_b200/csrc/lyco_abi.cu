@@ -783,7 +783,13 @@ int lyco_merge_weight(const lyco_delta_desc_t* d, const void* W, void* W_out, vo
       int grid = static_cast<int>((total + 255) / 256);
       const int cap = di.sms * 16;
       if (grid > cap) grid = cap;
-      lyco::merge_ia3_kernel<<<grid, 256, 0, stream>>>(*d, w, wo);
+      if (aligned16 && d->in_dim % 8 == 0) {
+        int wgrid = cdiv(d->out_dim, 8);
+        if (wgrid > cap) wgrid = cap;
+        lyco::merge_ia3_vec_kernel<<<wgrid, 256, 0, stream>>>(*d, w, wo);
+      } else {
+        lyco::merge_ia3_kernel<<<grid, 256, 0, stream>>>(*d, w, wo);
+      }
       break;
     }
     case LYCO_ALGO_RAW: {
@@ -867,7 +873,17 @@ int lyco_factor_grads(const lyco_delta_desc_t* d, const float* dW, const void* W
     case LYCO_ALGO_IA3: {
       if (!g0 || !W) return fail("lyco_factor_grads: ia3 needs g0 and W");
       const uint16_t* w = static_cast<const uint16_t*>(W);
-      if (!d->on_input) {
+      const bool vec = K % 8 == 0 && ((reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(dW)) & 15) == 0;
+      if (vec && !d->on_input) {
+        // g_w[n] = mult * sum_k dW'[n,k] W[n,k]: the same row reduction as DoRA's backward, 16-byte loads, no atomics
+        int wgrid = cdiv(N, 8);
+        if (wgrid > di.sms * 16) wgrid = di.sms * 16;
+        lyco::dora_reduce_rows_vec_kernel<1><<<wgrid, 256, 0, stream>>>(dW, w, g0, N, K, d->w_dtype, d->m_post2);
+      } else if (vec) {
+        LYCO_CUDA(cudaMemsetAsync(g0, 0, sizeof(float) * static_cast<size_t>(K / d->ia3_group), stream));
+        const dim3 cgrid(cdiv(K / 8, 256), cdiv(N, 32));
+        lyco::dora_reduce_cols_vec_kernel<1><<<cgrid, 256, 0, stream>>>(dW, w, g0, N, K, d->ia3_group, d->w_dtype, d->m_post2);
+      } else if (!d->on_input) {
         lyco::grad_ia3_kernel<<<cdiv(N, 8), 256, 0, stream>>>(*d, dW, w, g0);
       } else {
         LYCO_CUDA(cudaMemsetAsync(g0, 0, sizeof(float) * static_cast<size_t>(K / d->ia3_group), stream));
