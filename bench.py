@@ -884,6 +884,15 @@ def cpu_reference(args, budget_s=20.0, reps=3):
     import torch
     import torch.nn as nn
 
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU leg runs on rank 0 alone and is entitled to the host's
+    # cores ("all the host threads it can use"): restore torch's own default of one thread per physical core
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except Exception:  # noqa: BLE001
+        avail = os.cpu_count() or 1
+    want = max(1, avail // 2)
+    if torch.get_num_threads() < want and os.environ.get("OMP_NUM_THREADS", "") in ("", "1"):
+        torch.set_num_threads(want)
     threads = torch.get_num_threads()
     classes = _reference_module_factory()
     kind = "reference" if classes is not None else "port"
