@@ -241,6 +241,25 @@ int lyco_factor_grads(const lyco_delta_desc_t* d, const float* dW, const void* W
 int lyco_grad_prep(const float* dW, const void* P, void* G, int64_t n, float gscale, int dtype, void* stream);
 
 /* ------------------------------------------------------------------------- */
+/* LoHa: factor products, Hadamard product and merge in one tensor-core kernel */
+/* ------------------------------------------------------------------------- */
+
+/*
+ * P1 = w1a [N, r] · w1b [r, K'],  P2 = w2a [N, r] · w2b [r, K']  per 128 x 128 weight tile on tcgen05 (two TMEM
+ * accumulators; the factors are staged by TMA, r <= 64 is one k-block), then in the epilogue
+ *   mode 0:  W_out = rnd_w(W + chain(rnd(P1) * rnd(P2)))      W, out0 16-bit [N, K'] (w_dtype); chain multipliers
+ *            m_pre, m_post1, m_post2 as in lyco_delta_desc_t with the product domain = `dtype`
+ *   mode 1:  out0 = G1 = rnd(gscale * dW * rnd(P2)),  out1 = G2 = rnd(gscale * dW * rnd(P1))      W = dW' fp32 [N, K']
+ * so the [N, K'] products never travel through HBM (forward 4 instead of 12 bytes per weight element, backward 8
+ * instead of 20).  Factors in `dtype` (bf16 / f16), r % 8 == 0, 8 <= r <= 64, K' % 8 == 0, 16-byte aligned arrays.
+ * Replaces HadaWeight.forward and the re-products of HadaWeight.backward, lycoris/functional/loha.py:10-30, plus
+ * `.to(dtype) * scalar`, `W + dW * mult` of lycoris/modules/loha.py:310-318.
+ */
+int lyco_hada(int mode, const void* w1a, const void* w1b, const void* w2a, const void* w2b, const void* W,
+              void* out0, void* out1, int N, int K, int rank, int dtype, int w_dtype, float m_pre, float m_post1,
+              float m_post2, float gscale, void* stream);
+
+/* ------------------------------------------------------------------------- */
 /* structured LoKr factor gradients (no dense dW')                            */
 /* ------------------------------------------------------------------------- */
 

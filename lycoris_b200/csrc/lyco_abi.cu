@@ -17,6 +17,7 @@
 #include "layout_kernels.cuh"
 #include "lokr_struct_kernels.cuh"
 #include "dora_kernels.cuh"
+#include "hada_sm100.cuh"
 
 namespace {
 
@@ -911,6 +912,55 @@ int lyco_grad_prep(const float* dW, const void* P, void* G, int64_t n, float gsc
   if (grid > cap) grid = cap;
   lyco::grad_prep_kernel<<<grid, 256, 0, stream>>>(dW, static_cast<const uint16_t*>(P), static_cast<uint16_t*>(G), n / 8,
                                                    gscale, dtype);
+  LYCO_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+int lyco_hada(int mode, const void* w1a, const void* w1b, const void* w2a, const void* w2b, const void* W, void* out0,
+              void* out1, int N, int K, int rank, int dtype, int w_dtype, float m_pre, float m_post1, float m_post2,
+              float gscale, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (mode != 0 && mode != 1) return fail("lyco_hada: mode must be 0 (merge) or 1 (gradient operands)");
+  if (!w1a || !w1b || !w2a || !w2b || !W || !out0 || (mode == 1 && !out1)) return fail("lyco_hada: null operand");
+  if (dtype != LYCO_BF16 && dtype != LYCO_F16) return fail("lyco_hada: factors must be bf16/f16");
+  if (mode == 0 && w_dtype != LYCO_BF16 && w_dtype != LYCO_F16) return fail("lyco_hada: weights must be bf16/f16");
+  if (N <= 0 || K <= 0 || rank < 8 || rank > 64 || rank % 8 || K % 8)
+    return fail("lyco_hada: needs N, K > 0, K %% 8 == 0, rank in 8..64 and a multiple of 8 (N=%d K=%d rank=%d)", N, K, rank);
+  if ((reinterpret_cast<uintptr_t>(w1a) | reinterpret_cast<uintptr_t>(w1b) | reinterpret_cast<uintptr_t>(w2a) |
+       reinterpret_cast<uintptr_t>(w2b) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(out0) |
+       reinterpret_cast<uintptr_t>(out1)) & 15)
+    return fail("lyco_hada: arrays must be 16-byte aligned");
+  DeviceInfo di;
+  if (device_info(&di)) return 1;
+  CUtensorMap ta1, tb1, ta2, tb2;
+  if (make_tmap(&ta1, w1a, rank, N, rank, 64, lyco::HADA_BM)) return 1;   // [N, r]  K-major A
+  if (make_tmap(&ta2, w2a, rank, N, rank, 64, lyco::HADA_BM)) return 1;
+  if (make_tmap(&tb1, w1b, K, rank, K, 64, 64)) return 1;                 // [r, K'] MN-major B
+  if (make_tmap(&tb2, w2b, K, rank, K, 64, 64)) return 1;
+  lyco::HadaParams p;
+  p.W = W; p.out0 = out0; p.out1 = out1; p.N = N; p.K = K; p.rank = rank;
+  p.fmt = dtype == LYCO_BF16 ? 1 : 0; p.w_dtype = w_dtype;
+  p.m_pre = m_pre; p.m_post1 = m_post1; p.m_post2 = m_post2; p.gscale = gscale;
+  const int grid = cdiv(N, lyco::HADA_BM) * cdiv(K, lyco::HADA_BN);
+  static bool configured[2][64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (mode == 0) {
+    auto kern = lyco::hada_sm100_kernel<0>;
+    if (!configured[0][dev & 63]) {
+      LYCO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lyco::HADA_SMEM_BYTES));
+      configured[0][dev & 63] = true;
+    }
+    kern<<<grid, lyco::HADA_THREADS, lyco::HADA_SMEM_BYTES, stream>>>(ta1, tb1, ta2, tb2, p);
+  } else {
+    auto kern = lyco::hada_sm100_kernel<1>;
+    if (!configured[1][dev & 63]) {
+      LYCO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lyco::HADA_SMEM_BYTES));
+      configured[1][dev & 63] = true;
+    }
+    kern<<<grid, lyco::HADA_THREADS, lyco::HADA_SMEM_BYTES, stream>>>(ta1, tb1, ta2, tb2, p);
+  }
   LYCO_CUDA(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;

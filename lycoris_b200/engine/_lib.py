@@ -32,6 +32,7 @@ EXPORTED_SYMBOLS = (
     "lyco_merge_weight",
     "lyco_factor_grads",
     "lyco_grad_prep",
+    "lyco_hada",
     "lyco_lokr_mix",
     "lyco_lokr_w1grad",
     "lyco_delta_weight",
@@ -125,6 +126,11 @@ def _bind(lib):
     ]
     lib.lyco_grad_prep.restype = c_int
     lib.lyco_grad_prep.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_int, c_void_p]
+    lib.lyco_hada.restype = c_int
+    lib.lyco_hada.argtypes = [
+        c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,  # mode w1a w1b w2a w2b W out0 out1
+        c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_float, c_void_p,
+    ]
     lib.lyco_lokr_mix.restype = c_int
     lib.lyco_lokr_mix.argtypes = [
         c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,  # in out w w_dtype ldw transpose

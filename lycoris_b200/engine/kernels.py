@@ -313,6 +313,35 @@ def grad_prep(dW: torch.Tensor, P, gscale: float, dtype: torch.dtype) -> torch.T
     return G
 
 
+def hada_merge(f, W, m_pre, m_post1, m_post2):
+    """LoHa forward merge in one kernel: ``W' = rnd(W + chain((w1a·w1b) ⊙ (w2a·w2b)))`` — ``f`` = the four 16-bit factor
+    arrays ``[N,r], [r,K'], [N,r], [r,K']`` (lyco_hada mode 0)."""
+    _require_cuda(W, *f)
+    N, r = f[0].shape
+    Kp = f[1].shape[1]
+    out = torch.empty_like(W)
+    rc = _lib.load().lyco_hada(0, _ptr(f[0]), _ptr(f[1]), _ptr(f[2]), _ptr(f[3]), _ptr(W), _ptr(out), None, N, Kp, r,
+                               dtype_code(f[0].dtype), dtype_code(W.dtype), float(m_pre), float(m_post1), float(m_post2),
+                               1.0, _stream())
+    _lib.check(rc, "hada_merge")
+    return out
+
+
+def hada_grad_operands(f, dW, gscale):
+    """``(G1, G2) = (rnd(g·dW'·P2), rnd(g·dW'·P1))`` with P1, P2 recomputed on the tensor cores per tile (lyco_hada
+    mode 1): the 16-bit operands of LoHa's four skinny gradient contractions."""
+    _require_cuda(dW, *f)
+    assert dW.dtype == torch.float32 and dW.is_contiguous()
+    N, r = f[0].shape
+    Kp = f[1].shape[1]
+    G1 = torch.empty((N, Kp), device=dW.device, dtype=f[0].dtype)
+    G2 = torch.empty((N, Kp), device=dW.device, dtype=f[0].dtype)
+    rc = _lib.load().lyco_hada(1, _ptr(f[0]), _ptr(f[1]), _ptr(f[2]), _ptr(f[3]), _ptr(dW), _ptr(G1), _ptr(G2), N, Kp, r,
+                               dtype_code(f[0].dtype), dtype_code(f[0].dtype), 1.0, 1.0, 1.0, float(gscale), _stream())
+    _lib.check(rc, "hada_grad_operands")
+    return G1, G2
+
+
 def lokr_mix(x, w1, na, nb, nc, transpose, zero=None):
     """``out[m, a, c] = sum_b Wm(a, b) * x[m, b, c]`` with ``Wm = w1`` (or ``w1ᵀ``); ``x`` is a contiguous 16-bit
     ``[M, nb*nc]`` array, the result ``[M, na*nc]`` (lyco_lokr_mix).  ``zero``: optional contiguous fp32 tensor the
@@ -386,5 +415,5 @@ def dora_bwd(dW, Wm, dora_scale, sumsq, on_out, taps, mult, eps, want_scale_grad
 
 __all__ = [
     "gemm", "gemm_dual", "gemm_supported", "conv2d_supported", "as_nhwc", "conv2d_fprop", "conv2d_wgrad", "make_desc", "merge_weight", "factor_grads", "dtype_code",
-    "grad_prep", "lokr_mix", "lokr_w1grad", "delta_weight", "dora_fwd", "dora_bwd", "ALGO_LOCON", "ALGO_LOHA", "ALGO_LOKR", "ALGO_IA3", "ALGO_DYLORA", "ALGO_RAW", "BF16", "F16", "F32",
+    "grad_prep", "hada_merge", "hada_grad_operands", "lokr_mix", "lokr_w1grad", "delta_weight", "dora_fwd", "dora_bwd", "ALGO_LOCON", "ALGO_LOHA", "ALGO_LOKR", "ALGO_IA3", "ALGO_DYLORA", "ALGO_RAW", "BF16", "F16", "F32",
 ]

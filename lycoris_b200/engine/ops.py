@@ -247,10 +247,22 @@ def _lowrank_operands(spec, factors, prod):
     return [o.contiguous() for o in ops]
 
 
+# LoHa: one tensor-core kernel forms both factor products of a tile, multiplies them and merges (hada_sm100.cuh);
+# LYCO_LOHA=split keeps the round-1 sequence (two product GEMMs writing [N, K'] arrays + merge_raw / grad_prep).
+_LOHA_FUSED = os.environ.get("LYCO_LOHA", "fused") != "split"
+
+
+def _hada_ok(spec, f, W):
+    return (_LOHA_FUSED and spec.algo == K.ALGO_LOHA and 8 <= spec.rank <= 64 and spec.rank % 8 == 0
+            and W.numel() // W.shape[0] % 8 == 0 and f[0].dtype == W.dtype)
+
+
 def _lowrank_merge(spec, factors, W, prod, out_dim, in_dim, keep=None):
     f = _lowrank_operands(spec, factors, prod)
     if keep is not None:
         keep.extend(f)  # the 16-bit operand copies are reused by backward (4 cast kernels less per LoHa layer-step)
+    if _hada_ok(spec, f, W):
+        return K.hada_merge(f, W.view(out_dim, in_dim), spec.m_pre, spec.m_post1, spec.m_post2).view(W.shape)
     raws = [K.gemm(f[0], f[1], b_mn=True)]  # [N, r] x [r, K'] -> [N, K'], rounded to `prod` like the reference's matmul
     if spec.algo == K.ALGO_LOHA:
         raws.append(K.gemm(f[2], f[3], b_mn=True))
@@ -287,10 +299,13 @@ def _lowrank_grads(spec, factors, dWm, prod, f=None):
         if spec.algo == K.ALGO_DYLORA and spec.m_in != 1.0:
             g_down = g_down * spec.m_in
         return [g_up, g_down]
-    P1 = K.gemm(f[0], f[1], b_mn=True)  # recomputed, never cached (functional/loha.py:18-30)
-    P2 = K.gemm(f[2], f[3], b_mn=True)
-    G1 = K.grad_prep(dWm, P2, gscale, prod)
-    G2 = K.grad_prep(dWm, P1, gscale, prod)
+    if _LOHA_FUSED and 8 <= r <= 64 and Kp % 8 == 0:
+        G1, G2 = K.hada_grad_operands(f, dWm, gscale)  # P1, P2 re-formed per tile on the tensor cores, never stored
+    else:
+        P1 = K.gemm(f[0], f[1], b_mn=True)  # recomputed, never cached (functional/loha.py:18-30)
+        P2 = K.gemm(f[2], f[3], b_mn=True)
+        G1 = K.grad_prep(dWm, P2, gscale, prod)
+        G2 = K.grad_prep(dWm, P1, gscale, prod)
     g = _zeroed_views([(N, r), (r, Kp), (N, r), (r, Kp)], dWm.device)
     K.gemm(G1, f[1], out=g[0], out_dtype=f32, accumulate=True)
     K.gemm(f[0], G1, a_mn=True, b_mn=True, out=g[1], out_dtype=f32, accumulate=True)

@@ -273,6 +273,73 @@ def test_locon_conv_skinny_factor_gradients_match_dense_path(C, O, k, stride, si
     assert rel_err(gds, gdd) <= 2e-2, ("down", rel_err(gds, gdd))
 
 
+# ------------------------------------------------------------------------------------------ LoHa fused tile kernel
+@pytest.mark.parametrize("N,K,r", [(1280, 1280, 32), (10240, 1280, 32), (1280, 11520, 16), (200, 72, 8), (320, 2880, 64),
+                                   (96, 64, 8)])
+def test_hada_kernels_are_bit_identical_to_the_split_sequence(N, K, r):
+    """lyco_hada forms (w1a·w1b) ⊙ (w2a·w2b) per tile in TMEM and merges / builds the gradient operands in the epilogue;
+    the round-1 sequence wrote both products with lyco_gemm and read them back in merge_raw / grad_prep.  Same MMA, same
+    rounding points -> the results must be BIT-identical, ragged tile edges included."""
+    from lycoris_b200.engine import kernels as Kk
+
+    g = torch.Generator().manual_seed(0)
+    f = [(torch.randn(N, r, generator=g) * 0.2).cuda().to(torch.bfloat16), (torch.randn(r, K, generator=g) * 0.2).cuda().to(torch.bfloat16),
+         (torch.randn(N, r, generator=g) * 0.2).cuda().to(torch.bfloat16), (torch.randn(r, K, generator=g) * 0.2).cuda().to(torch.bfloat16)]
+    W = (torch.randn(N, K, generator=g) * 0.05).cuda().to(torch.bfloat16)
+    m = (0.5, 1.0, 0.75)
+    fused = Kk.hada_merge(f, W, *m)
+    P1 = Kk.gemm(f[0], f[1], b_mn=True)
+    P2 = Kk.gemm(f[2], f[3], b_mn=True)
+    desc = Kk.make_desc(Kk.ALGO_RAW, N, K, factors=[P1, P2], w_dtype=W.dtype, pre_round=1, pre_dtype=torch.bfloat16,
+                        m_pre=m[0], m_post1=m[1], m_post2=m[2])
+    split = Kk.merge_weight(desc, W)
+    assert torch.equal(fused, split), float((fused.float() - split.float()).abs().max())
+    ref = (W.float() + (f[0].float() @ f[1].float()) * (f[2].float() @ f[3].float()) * (m[0] * m[1] * m[2]))
+    assert float((fused.float() - ref).abs().max()) <= 2.0 ** -6 * float(ref.abs().max())
+    dW = torch.randn(N, K, generator=g).cuda()
+    G1, G2 = Kk.hada_grad_operands(f, dW, 0.3)
+    assert torch.equal(G1, Kk.grad_prep(dW, P2, 0.3, torch.bfloat16))
+    assert torch.equal(G2, Kk.grad_prep(dW, P1, 0.3, torch.bfloat16))
+
+
+def test_loha_layer_fused_vs_split_paths_agree():
+    import lycoris_b200 as L
+    from lycoris_b200.engine import ops
+
+    torch.manual_seed(0)
+    base = nn.Linear(1280, 2560).cuda().to(torch.bfloat16)
+    base.requires_grad_(False)
+    mod = L.LohaModule("t", base, 0.9, 32, 16).cuda()
+    gen = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for p in mod.parameters():
+            p.copy_((torch.randn(p.shape, generator=gen) * 0.1).to(p))
+    x = torch.randn(4096, 1280, generator=gen).cuda().to(torch.bfloat16)
+    dy = (torch.randn(4096, 2560, generator=gen) * 0.1).cuda().to(torch.bfloat16)
+    mod.apply_to()
+
+    def run(fused):
+        saved = ops._LOHA_FUSED
+        ops._LOHA_FUSED = fused
+        try:
+            for p in mod.parameters():
+                p.grad = None
+            xe = x.clone().requires_grad_(True)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                y = base(xe)
+            y.backward(dy)
+            return y.detach(), xe.grad, {k: p.grad.clone() for k, p in mod.named_parameters()}
+        finally:
+            ops._LOHA_FUSED = saved
+
+    yf, dxf, gf = run(True)
+    ys, dxs, gs = run(False)
+    mod.restore()
+    assert torch.equal(yf, ys) and torch.equal(dxf, dxs)
+    for k in gs:
+        assert rel_err(gf[k], gs[k]) <= 1e-3, (k, rel_err(gf[k], gs[k]))  # split-K atomics order only
+
+
 # ------------------------------------------------------------------------------------------ delta weight
 def _mods(dtype):
     import lycoris_b200 as L
