@@ -99,110 +99,82 @@ hada_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a1, const __grid_cons
     }
     ptx::umma_commit(mma_bar);
   }
-  // ------------------------------------------------------------------ epilogue: this thread owns weight row `row`
-  // Its 128 columns of W (256 contiguous bytes; MODE 1: the first 32 columns of the fp32 dW') are REQUESTED NOW, before
-  // the wait for the tensor-core products: the global-load latency hides behind TMA + MMA instead of following them.
-  const int row = m0 + warp * 32 + lane;
-  const bool fast = row < p.N && n0 + HADA_BN <= p.K && (p.K & 7) == 0;  // whole 128-column row segment, 16-byte aligned
-  const int64_t row_off = static_cast<int64_t>(row) * p.K + n0;
-  uint4 wpre[MODE == 0 ? 16 : 1];
-  float4 gcur[MODE == 1 ? 8 : 1];
-  if (fast) {
-    if (MODE == 0) {
-      const uint4* wp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.W) + row_off);
-#pragma unroll
-      for (int q = 0; q < 16; ++q) wpre[q] = __ldg(wp + q);
-    } else {
-      const float4* gp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.W) + row_off);
-#pragma unroll
-      for (int q = 0; q < 8; ++q) gcur[q] = __ldg(gp + q);
-    }
-  }
   __syncwarp();
   ptx::mbar_wait(mma_bar, 0);
   ptx::tc_fence_after();
 
+  // ------------------------------------------------------------------ epilogue: this thread owns weight row `row`
+  const int row = m0 + warp * 32 + lane;
   const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
   const int pd = p.fmt == 1 ? LYCO_BF16 : LYCO_F16;  // product dtype
   const Chain ch{1, pd, p.w_dtype, p.m_pre, p.m_post1, p.m_post2};
-#pragma unroll
+#pragma unroll 1
   for (int c = 0; c < HADA_BN / 32; ++c) {
     uint32_t r1[32], r2[32];
     ptx::tmem_ld_32x32(t_row + c * 32, r1);
     ptx::tmem_ld_32x32(t_row + HADA_BN + c * 32, r2);
     const int col0 = n0 + c * 32;
-    float4 gnext[MODE == 1 ? 8 : 1];
-    if (MODE == 1 && fast && c + 1 < HADA_BN / 32) {
-      const float4* gp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.W) + row_off + (c + 1) * 32);
+    if (row >= p.N || col0 >= p.K) continue;
+    const int64_t off = static_cast<int64_t>(row) * p.K + col0;
+    const int ncols = min(32, p.K - col0);
+    if (MODE == 0) {
+      const uint16_t* w = reinterpret_cast<const uint16_t*>(p.W) + off;
+      uint16_t* o = reinterpret_cast<uint16_t*>(p.out0) + off;
+      if (ncols == 32 && (p.K & 7) == 0) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) gnext[q] = __ldg(gp + q);  // next chunk in flight while this one is consumed
-    }
-    if (row < p.N && col0 < p.K) {
-      const int64_t off = static_cast<int64_t>(row) * p.K + col0;
-      const int ncols = min(32, p.K - col0);
-      if (MODE == 0) {
-        const uint16_t* w = reinterpret_cast<const uint16_t*>(p.W) + off;
-        uint16_t* o = reinterpret_cast<uint16_t*>(p.out0) + off;
-        if (fast || (ncols == 32 && (p.K & 7) == 0)) {
+        for (int q = 0; q < 4; ++q) {
+          const uint4 wv = __ldg(reinterpret_cast<const uint4*>(w) + q);
+          const uint16_t* wh = reinterpret_cast<const uint16_t*>(&wv);
+          uint4 ov;
+          uint16_t* oh = reinterpret_cast<uint16_t*>(&ov);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint4 wv = fast ? wpre[4 * c + q] : __ldg(reinterpret_cast<const uint4*>(w) + q);
-            const uint16_t* wh = reinterpret_cast<const uint16_t*>(&wv);
-            uint4 ov;
-            uint16_t* oh = reinterpret_cast<uint16_t*>(&ov);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float raw = rnd(__uint_as_float(r1[8 * q + j]), pd) * rnd(__uint_as_float(r2[8 * q + j]), pd);
-              oh[j] = to16(merged(cvt16(wh[j], p.w_dtype), apply_chain(raw, ch), p.w_dtype), p.w_dtype);
-            }
-            reinterpret_cast<uint4*>(o)[q] = ov;
+          for (int j = 0; j < 8; ++j) {
+            const float raw = rnd(__uint_as_float(r1[8 * q + j]), pd) * rnd(__uint_as_float(r2[8 * q + j]), pd);
+            oh[j] = to16(merged(cvt16(wh[j], p.w_dtype), apply_chain(raw, ch), p.w_dtype), p.w_dtype);
           }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {  // fully unrolled with a predicate: r1 / r2 stay in registers
-            if (j < ncols) {
-              const float raw = rnd(__uint_as_float(r1[j]), pd) * rnd(__uint_as_float(r2[j]), pd);
-              o[j] = to16(merged(cvt16(w[j], p.w_dtype), apply_chain(raw, ch), p.w_dtype), p.w_dtype);
-            }
-          }
+          reinterpret_cast<uint4*>(o)[q] = ov;
         }
       } else {
-        const float* g = reinterpret_cast<const float*>(p.W) + off;
-        uint16_t* o1 = reinterpret_cast<uint16_t*>(p.out0) + off;
-        uint16_t* o2 = reinterpret_cast<uint16_t*>(p.out1) + off;
-        if (fast || (ncols == 32 && (p.K & 7) == 0)) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 g0 = fast ? gcur[2 * q] : __ldg(reinterpret_cast<const float4*>(g) + 2 * q);
-            const float4 g1 = fast ? gcur[2 * q + 1] : __ldg(reinterpret_cast<const float4*>(g) + 2 * q + 1);
-            const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-            uint4 v1, v2;
-            uint16_t* h1 = reinterpret_cast<uint16_t*>(&v1);
-            uint16_t* h2 = reinterpret_cast<uint16_t*>(&v2);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float sg = gv[j] * p.gscale;
-              h1[j] = to16(sg * rnd(__uint_as_float(r2[8 * q + j]), pd), pd);
-              h2[j] = to16(sg * rnd(__uint_as_float(r1[8 * q + j]), pd), pd);
-            }
-            reinterpret_cast<uint4*>(o1)[q] = v1;
-            reinterpret_cast<uint4*>(o2)[q] = v2;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (j < ncols) {
-              const float sg = g[j] * p.gscale;
-              o1[j] = to16(sg * rnd(__uint_as_float(r2[j]), pd), pd);
-              o2[j] = to16(sg * rnd(__uint_as_float(r1[j]), pd), pd);
-            }
+        for (int j = 0; j < 32; ++j) {  // fully unrolled with a predicate: r1 / r2 stay in registers
+          if (j < ncols) {
+            const float raw = rnd(__uint_as_float(r1[j]), pd) * rnd(__uint_as_float(r2[j]), pd);
+            o[j] = to16(merged(cvt16(w[j], p.w_dtype), apply_chain(raw, ch), p.w_dtype), p.w_dtype);
           }
         }
       }
-    }
-    if (MODE == 1 && fast) {
+    } else {
+      const float* g = reinterpret_cast<const float*>(p.W) + off;
+      uint16_t* o1 = reinterpret_cast<uint16_t*>(p.out0) + off;
+      uint16_t* o2 = reinterpret_cast<uint16_t*>(p.out1) + off;
+      if (ncols == 32 && (p.K & 7) == 0) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) gcur[q] = gnext[q];
+        for (int q = 0; q < 4; ++q) {
+          const float4 g0 = __ldg(reinterpret_cast<const float4*>(g) + 2 * q);
+          const float4 g1 = __ldg(reinterpret_cast<const float4*>(g) + 2 * q + 1);
+          const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+          uint4 v1, v2;
+          uint16_t* h1 = reinterpret_cast<uint16_t*>(&v1);
+          uint16_t* h2 = reinterpret_cast<uint16_t*>(&v2);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float s = gv[j] * p.gscale;
+            h1[j] = to16(s * rnd(__uint_as_float(r2[8 * q + j]), pd), pd);
+            h2[j] = to16(s * rnd(__uint_as_float(r1[8 * q + j]), pd), pd);
+          }
+          reinterpret_cast<uint4*>(o1)[q] = v1;
+          reinterpret_cast<uint4*>(o2)[q] = v2;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (j < ncols) {
+            const float s = g[j] * p.gscale;
+            o1[j] = to16(s * rnd(__uint_as_float(r2[j]), pd), pd);
+            o2[j] = to16(s * rnd(__uint_as_float(r1[j]), pd), pd);
+          }
+        }
+      }
     }
   }
 
