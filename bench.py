@@ -437,10 +437,11 @@ def run_engine(args):
 
     # instrumented eager steps: CUDA-event pair around every lyco_gemm launch (same stream)
     sink = []
-    K.set_gemm_profiler(sink)
+    # keep the GPU busy for ~0.6 s first so the host runs ahead of it, and again for 4 ms before every 32nd bracket
+    # (outside the brackets): the event pairs then bracket kernel execution on a busy stream, not the GPU waiting for
+    # the (slower) eager Python launch path — on a host-bound box the brackets otherwise count host time
+    K.set_gemm_profiler(sink, refill_every=32, refill_cycles=int(4e-3 * 1.9e9))
     l0 = _lib.launch_count()
-    # keep the GPU busy for ~0.6 s first so the host runs ahead of it: the event pairs then bracket kernel
-    # execution on the stream, not the GPU waiting for the (slower) eager Python launch path
     torch.cuda._sleep(int(0.6 * 1.9e9))
     step()
     torch.cuda.synchronize()
@@ -555,6 +556,9 @@ def run_engine(args):
             # the event brackets above also contain the split-K memsets and the stream front-end gap per launch;
             # the same launches by CUPTI kernel duration (torch.profiler over one eager step):
             "gemm_kernel_ms_per_step_cupti": gemm_kernel_ms,
+            # all event brackets (tensor-bound + HBM-bound launches) over the CUPTI kernel time of the same launches:
+            # ~1.1 when the brackets hold kernels only, well above when the eager step was host-bound
+            "event_ms_over_cupti_ms": ((gemm_ms + skinny_ms) / gemm_kernel_ms) if gemm_kernel_ms else None,
             # (CUPTI totals cannot be split by shape: ALL gemm_sm100_kernel launches, tensor-bound and HBM-bound alike)
             "achieved_cupti_all_gemm_launches": ((gemm_flops + skinny_flops) / (gemm_kernel_ms * 1e-3) / 1e12) if gemm_kernel_ms else None,
             # ALGORITHMIC work of the adapter path (c*F1 + F_side, c = 2 or 3 — never the

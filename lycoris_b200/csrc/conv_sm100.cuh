@@ -69,7 +69,8 @@ conv_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   uint64_t* empty_bar = full_bar + GEMM_MAX_STAGES;
   uint64_t* tfull_bar = empty_bar + GEMM_MAX_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* tlast_bar = tempty_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tlast_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -85,8 +86,10 @@ conv_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     ptx::prefetch_tmap(&tmap_b);
     if (epi_uses_tma(EPI)) ptx::prefetch_tmap(&tmap_c);
   }
-  gemm_setup<PAIR>(full_bar, empty_bar, tfull_bar, tempty_bar, tmem_slot, stages, warp, lane);
+  gemm_setup<PAIR>(full_bar, empty_bar, tfull_bar, tempty_bar, tlast_bar, tmem_slot, stages, warp, lane);
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();     // everything above overlapped the previous kernel; its results are visible from here (pdl.cuh)
+  pdl_trigger();
 
   const int workers = PAIR ? (gridDim.x >> 1) : gridDim.x;
   const int worker = PAIR ? (blockIdx.x >> 1) : blockIdx.x;
@@ -182,6 +185,10 @@ conv_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
       if (PAIR) ptx::umma_commit_pair(&tfull_bar[acc], 0b11);
       else ptx::umma_commit(&tfull_bar[acc]);
+      if (it.last()) {  // wakes warps 0..3 for their share of the last drain (gemm_last_unit_helper)
+        if (PAIR) ptx::umma_commit_pair(tlast_bar, 0b11);
+        else ptx::umma_commit(tlast_bar);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -208,12 +215,35 @@ conv_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       ptx::tc_fence_after();
       const int row0 = m_idx * rows_per_tile + static_cast<int>(rank) * GEMM_BLOCK_M + ew * 32;
       const uint32_t t_row = tmem_base + acc * 256 + (static_cast<uint32_t>(ew * 32) << 16);
-      gemm_epilogue_tile<PAIR, EPI>(t_row, row0, col_base, col_limit, block_n, p, &tmap_c, stage_buf, buf,
+      const int chunks = it.last() ? main_chunks_of_last_unit(block_n) : (block_n >> 5);
+      gemm_epilogue_tile<PAIR, EPI>(t_row, row0, col_base, col_limit, 0, chunks, p, &tmap_c, stage_buf, buf,
                                     &tempty_bar[acc], lane);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
     if (epi_uses_tma(EPI) && lane == 0) ptx::tma_store_wait_read<0>();
+  }
+
+  if (warp < 4) {
+    __syncwarp();
+    const int total = p.m_tiles * p.n_tiles * p.splits;
+    if (worker < total) {
+      const int u = (total - worker + workers - 1) / workers - 1;  // this worker's last unit
+      const int tile = (worker + u * workers) / p.splits;
+      const int n_idx = tile % p.n_tiles, m_idx = tile / p.n_tiles;
+      int col_base, col_limit;
+      if (MODE == MODE_FPROP) {
+        col_base = n_idx * block_n;
+        col_limit = p.N;
+      } else {
+        const int tap = n_idx / cp.tiles_per_tap;
+        col_base = tap * cp.C + (n_idx - tap * cp.tiles_per_tap) * block_n;
+        col_limit = (tap + 1) * cp.C;
+      }
+      const int row0 = m_idx * rows_per_tile + static_cast<int>(rank) * GEMM_BLOCK_M + warp * 32;
+      gemm_last_unit_helper<PAIR, EPI>(tmem_base, u & 1, row0, col_base, col_limit, block_n, p, &tmap_c, smem, tlast_bar,
+                                       warp, lane);
+    }
   }
 
   gemm_teardown<PAIR>(tmem_base, warp);

@@ -7,7 +7,7 @@
 //   warp 1      MMA issuer    (one elected lane)      tcgen05.mma, D in TMEM
 //   warp 2      TMEM allocator / deallocator
 //   warps 4..7  epilogue: tcgen05.ld -> registers -> (bias, cast) -> swizzled smem -> TMA store
-//               (fp32 outputs: direct 16-byte stores / red.global.add.v4.f32 for split-K partials)
+//               (fp32 outputs: the same staging, TMA store or TMA reduce-add for split-K partials)
 // Three pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue, two accumulator
 // stages so the epilogue of tile i overlaps the main loop of tile i+1), and the static persistent
 // tile schedule.  BLOCK_N is a RUNTIME multiple of 32 (32..256) picked per problem by the host so
@@ -28,6 +28,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include "pdl.cuh"
 #include "ptx_sm100.cuh"
 
 namespace lyco {
@@ -45,7 +46,7 @@ constexpr int GEMM_TMEM_COLS = 512;            // two accumulator stages at colu
 constexpr int GEMM_SMEM_BYTES = GEMM_RING_BYTES + GEMM_EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
 enum { EPI_STORE16 = 0, EPI_STORE_F32 = 1, EPI_ATOMIC_F32 = 2, EPI_STORE16_NCHW = 3, EPI_STORE_F32_NCHW = 4 };
-__host__ __device__ constexpr bool epi_uses_tma(int epi) { return epi == EPI_STORE16 || epi == EPI_STORE16_NCHW; }
+__host__ __device__ constexpr bool epi_uses_tma(int epi) { return epi != EPI_STORE_F32_NCHW; }
 
 struct GemmParams {
   void* C;
@@ -60,7 +61,27 @@ struct GemmParams {
   int fmt;          // operand / 16-bit output format: 0 = f16, 1 = bf16
   int bias_dtype;   // LYCO_BF16 / LYCO_F16 / LYCO_F32
   int epi_pq;       // EPI_STORE16_NCHW: output pixels per image (rows of C are (image, pixel); multiple of 32)
+#ifdef LYCO_GEMM_TRACE
+  unsigned long long* trace;  // debug build only (tools/gemm_trace.py): 64 clock64 slots per CTA
+#endif
 };
+
+// Timeline probes of the debug build: slot 0 entry, 1 globaltimer at entry, 2 setup done, 3 first TMA issued,
+// 4 first operand stage landed, 5 last TMA issued, 6 last MMA commit issued, 8+2i / 9+2i accumulator i ready / drained
+// (epilogue warp 4), 40 exit, 41 globaltimer at exit, 42 tiles of this CTA.  Compiled out of the product library.
+#ifdef LYCO_GEMM_TRACE
+#define LYCO_TRACE(slot, value)                                                            \
+  do {                                                                                      \
+    if (p.trace) p.trace[static_cast<size_t>(blockIdx.x) * 64 + (slot)] = (value);          \
+  } while (0)
+__device__ __forceinline__ unsigned long long trace_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#else
+#define LYCO_TRACE(slot, value) do {} while (0)
+#endif
 
 __device__ __forceinline__ float load_scalar(const void* p, int dtype, int64_t i) {
   if (dtype == 2) return reinterpret_cast<const float*>(p)[i];
@@ -110,33 +131,42 @@ __device__ __forceinline__ void add_bias32(float (&v)[32], const GemmParams& p, 
   }
 }
 
-// fp32 epilogue for one 32-column chunk of one accumulator row (plain store or split-K reduction)
+// fp32 epilogue for one 32-column chunk of this warp's 32 rows (plain store, or the reduction of split-K partials /
+// accumulate mode): two 16-column halves, each staged as a SWIZZLE_64B tile (32 rows x 64 B, the layout of the 16-bit
+// epilogue) and written by ONE TMA operation — cp.async.bulk.tensor store or cp.reduce.async.bulk.tensor .add.  The
+// round-1 epilogue issued one 16-byte red.global per lane and row (32 different lines per warp instruction): the drain
+// of a 256-column accumulator took 6.4 us and held the next unit's main loop back (tools/gemm_trace.py, wgrad
+// 1280 x 1280 x 8192).  The TMA unit clips at M / N; `n_limit` (the tap boundary of the convolution's weight gradient,
+// a multiple of 64 columns) only ever drops whole halves.
 template <int EPI>
-__device__ __forceinline__ void store_chunk_f32(const uint32_t (&r)[32], int row, int col0, const GemmParams& p,
-                                                int n_limit) {
-  if (row >= p.M || col0 >= n_limit) return;
-  float* crow = reinterpret_cast<float*>(p.C) + static_cast<int64_t>(row) * p.ldc + col0;
-  if (col0 + 32 <= n_limit) {
+__device__ __forceinline__ void store_chunk_f32(const uint32_t (&r)[32], int row0, int col0, const GemmParams& p,
+                                                int n_limit, const CUtensorMap* tmap_c, uint8_t* stage, int& buf,
+                                                int lane) {
+  if (row0 >= p.M) return;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      if (EPI == EPI_STORE_F32) {
-        reinterpret_cast<float4*>(crow)[q] =
-            make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
-                        __uint_as_float(r[4 * q + 3]));
-      } else {
-        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow + 4 * q),
-                     "f"(__uint_as_float(r[4 * q])), "f"(__uint_as_float(r[4 * q + 1])),
-                     "f"(__uint_as_float(r[4 * q + 2])), "f"(__uint_as_float(r[4 * q + 3]))
-                     : "memory");
-      }
+  for (int h = 0; h < 2; ++h) {
+    const int c0 = col0 + 16 * h;
+    if (c0 >= n_limit) break;  // warp-uniform; a skipped half commits no bulk group (see store_chunk_tma)
+    if (lane == 0) ptx::tma_store_wait_read<1>();
+    __syncwarp();
+    uint8_t* tile = stage + buf * 2048;
+    const uint32_t base = ptx::smem_u32(tile) + lane * 64;
+    const uint32_t sw = (lane >> 1) & 3;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t a = base + ((q ^ sw) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(r[16 * h + 4 * q]),
+                   "r"(r[16 * h + 4 * q + 1]), "r"(r[16 * h + 4 * q + 2]), "r"(r[16 * h + 4 * q + 3])
+                   : "memory");
     }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (col0 + j < n_limit) {
-        if (EPI == EPI_STORE_F32) crow[j] = __uint_as_float(r[j]);
-        else atomicAdd(crow + j, __uint_as_float(r[j]));
-      }
+    ptx::fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      if (EPI == EPI_ATOMIC_F32) ptx::tma_reduce_add_2d(tmap_c, tile, c0, row0);
+      else ptx::tma_store_2d(tmap_c, tile, c0, row0);
+      ptx::tma_store_commit();
+    }
+    buf ^= 1;
   }
 }
 
@@ -244,12 +274,23 @@ struct WorkIter {
     w += step;
     return true;
   }
+  // true when the unit next() just returned is this worker's last one
+  __device__ __forceinline__ bool last() const { return w >= total; }
 };
+
+// The LAST unit of a CTA has nothing to hide its drain behind (2.5 us of a 27 us launch at 8192 x 1280 x 1280,
+// tools/gemm_trace.py), and by then warps 0..3 (producer, MMA issuer, TMEM allocator, spare) are idle: they take the
+// upper half of the accumulator's column chunks — warp w reads the same TMEM lanes as epilogue warp 4 + w — staging
+// through the operand ring, which is dead once the last accumulator is complete.  `tlast_bar` is committed by the MMA
+// issuer together with the last tfull barrier; it completes exactly once, so the helpers need no phase bookkeeping.
+__device__ __forceinline__ int main_chunks_of_last_unit(int block_n) { return ((block_n >> 5) + 1) >> 1; }
 
 template <bool PAIR>
 __device__ __forceinline__ void gemm_setup(uint64_t* full_bar, uint64_t* empty_bar, uint64_t* tfull_bar,
-                                           uint64_t* tempty_bar, uint32_t* tmem_slot, int stages, int warp, int lane) {
+                                           uint64_t* tempty_bar, uint64_t* tlast_bar, uint32_t* tmem_slot, int stages,
+                                           int warp, int lane) {
   if (warp == 1 && lane == 0) {
+    ptx::mbar_init(tlast_bar, 1);
     for (int s = 0; s < stages; ++s) {
       ptx::mbar_init(&full_bar[s], PAIR ? 2 : 1);
       ptx::mbar_init(&empty_bar[s], 1);
@@ -303,17 +344,17 @@ __device__ __forceinline__ void gemm_issue_kblock(uint32_t sa, uint32_t sb, uint
 }
 
 // Drain one accumulator (this warp's 32 rows x block_n columns) from TMEM and write it out.
+// Chunks [c_begin, c_end) of 32 columns; `tempty_slot` != nullptr: arrive on it after this warp's last TMEM read.
 template <bool PAIR, int EPI>
-__device__ __forceinline__ void gemm_epilogue_tile(uint32_t t_row, int row0, int col_base, int n_limit, int block_n,
-                                                   const GemmParams& p, const CUtensorMap* tmap_c, uint8_t* stage,
-                                                   int& buf, uint64_t* tempty_slot, int lane) {
-  const int chunks = block_n >> 5;
+__device__ __forceinline__ void gemm_epilogue_tile(uint32_t t_row, int row0, int col_base, int n_limit, int c_begin,
+                                                   int c_end, const GemmParams& p, const CUtensorMap* tmap_c,
+                                                   uint8_t* stage, int& buf, uint64_t* tempty_slot, int lane) {
 #pragma unroll 1
-  for (int c = 0; c < chunks; ++c) {
+  for (int c = c_begin; c < c_end; ++c) {
     uint32_t r[32];
     ptx::tmem_ld_32x32(t_row + c * 32, r);
     ptx::tmem_ld_wait();
-    if (c == chunks - 1) {
+    if (tempty_slot != nullptr && c == c_end - 1) {
       // all of this warp's TMEM reads are done: hand the accumulator back to the MMA thread
       ptx::tc_fence_before();
       __syncwarp();
@@ -326,8 +367,24 @@ __device__ __forceinline__ void gemm_epilogue_tile(uint32_t t_row, int row0, int
     if (EPI == EPI_STORE16) store_chunk_tma(r, row0, col0, p, n_limit, tmap_c, stage, buf, lane);
     else if (EPI == EPI_STORE16_NCHW) store_chunk_tma_nchw(r, row0, col0, p, n_limit, tmap_c, stage, buf, lane);
     else if (EPI == EPI_STORE_F32_NCHW) store_chunk_f32_nchw(r, row0, col0, p, n_limit, lane);
-    else store_chunk_f32<EPI>(r, row0 + lane, col0, p, n_limit);
+    else store_chunk_f32<EPI>(r, row0, col0, p, n_limit, tmap_c, stage, buf, lane);
   }
+}
+
+// Warps 0..3 after their roles: upper column chunks of the CTA's last unit (see main_chunks_of_last_unit).
+template <bool PAIR, int EPI>
+__device__ __forceinline__ void gemm_last_unit_helper(uint32_t tmem_base, int acc, int row0, int col_base, int n_limit,
+                                                      int block_n, const GemmParams& p, const CUtensorMap* tmap_c,
+                                                      uint8_t* ring, uint64_t* tlast_bar, int warp, int lane) {
+  const int chunks = block_n >> 5, c0 = main_chunks_of_last_unit(block_n);
+  if (c0 >= chunks) return;
+  ptx::mbar_wait_parked(tlast_bar, 0, lane);
+  ptx::tc_fence_after();
+  const uint32_t t_row = tmem_base + acc * 256 + (static_cast<uint32_t>(warp * 32) << 16);
+  int buf = 0;
+  gemm_epilogue_tile<PAIR, EPI>(t_row, row0, col_base, n_limit, c0, chunks, p, tmap_c, ring + warp * 4096, buf,
+                                nullptr, lane);
+  if (epi_uses_tma(EPI) && lane == 0) ptx::tma_store_wait_read<0>();
 }
 
 template <bool PAIR, bool A_MN, bool B_MN, int EPI>
@@ -343,7 +400,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   uint64_t* empty_bar = full_bar + GEMM_MAX_STAGES;
   uint64_t* tfull_bar = empty_bar + GEMM_MAX_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* tlast_bar = tempty_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tlast_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -363,8 +421,17 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       ptx::prefetch_tmap(&tmap_b2);
     }
   }
-  gemm_setup<PAIR>(full_bar, empty_bar, tfull_bar, tempty_bar, tmem_slot, stages, warp, lane);
+#ifdef LYCO_GEMM_TRACE
+  if (threadIdx.x == 0) {
+    LYCO_TRACE(0, clock64());
+    LYCO_TRACE(1, trace_globaltimer());
+  }
+#endif
+  gemm_setup<PAIR>(full_bar, empty_bar, tfull_bar, tempty_bar, tlast_bar, tmem_slot, stages, warp, lane);
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();     // everything above overlapped the previous kernel; its results are visible from here (pdl.cuh)
+  pdl_trigger();
+  if (threadIdx.x == 0) LYCO_TRACE(2, clock64());
 
   const int workers = PAIR ? (gridDim.x >> 1) : gridDim.x;
   const int worker = PAIR ? (blockIdx.x >> 1) : blockIdx.x;
@@ -373,6 +440,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     // ------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
+    LYCO_TRACE(3, clock64());
     for (WorkIter it(p, worker, workers); it.next();) {
       const int n_idx = it.tile % p.n_tiles;
       const int m_idx = it.tile / p.n_tiles;
@@ -423,6 +491,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         if (++stage == stages) { stage = 0; phase ^= 1; }
       }
     }
+    LYCO_TRACE(5, clock64());
   } else if (warp == 1 && lane == 0 && rank == 0) {
     // ------------------------------------------------- MMA issuer (leader CTA only for a pair)
     const uint32_t idesc = ptx::make_idesc_f16(p.fmt, rows_per_tile, block_n, A_MN ? 1 : 0, B_MN ? 1 : 0);
@@ -430,6 +499,9 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+#ifdef LYCO_GEMM_TRACE
+    bool trace_first = false;
+#endif
     for (WorkIter it(p, worker, workers); it.next();) {
       const int kb0 = it.kb0, kb1 = it.kb1;
       ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -438,15 +510,23 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       for (int kb = kb0; kb < kb1; ++kb) {
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after();
+#ifdef LYCO_GEMM_TRACE
+        if (!trace_first) { trace_first = true; LYCO_TRACE(4, clock64()); }
+#endif
         const uint32_t sa = ptx::smem_u32(smem + stage * stage_bytes);
         gemm_issue_kblock<PAIR, A_MN, B_MN>(sa, sa + GEMM_A_BYTES, d_tmem, idesc, kb == kb0, &empty_bar[stage]);
         if (++stage == stages) { stage = 0; phase ^= 1; }
       }
       if (PAIR) ptx::umma_commit_pair(&tfull_bar[acc], 0b11);  // accumulator halves complete in both CTAs
       else ptx::umma_commit(&tfull_bar[acc]);
+      if (it.last()) {
+        if (PAIR) ptx::umma_commit_pair(tlast_bar, 0b11);
+        else ptx::umma_commit(tlast_bar);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    LYCO_TRACE(6, clock64());
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue
     const int ew = warp - 4;  // == warp % 4 -> TMEM lanes [32*ew, 32*ew + 32)
@@ -454,22 +534,55 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     int buf = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+#ifdef LYCO_GEMM_TRACE
+    int trace_tile = 0;
+#endif
     for (WorkIter it(p, worker, workers); it.next();) {
       const int n_idx = it.tile % p.n_tiles;
       const int m_idx = it.tile / p.n_tiles;
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tc_fence_after();
+#ifdef LYCO_GEMM_TRACE
+      if (ew == 0 && lane == 0 && trace_tile < 16) LYCO_TRACE(8 + 2 * trace_tile, clock64());
+#endif
       const int row0 = m_idx * rows_per_tile + static_cast<int>(rank) * GEMM_BLOCK_M + ew * 32;
       const uint32_t t_row = tmem_base + acc * 256 + (static_cast<uint32_t>(ew * 32) << 16);
-      gemm_epilogue_tile<PAIR, EPI>(t_row, row0, n_idx * block_n, p.N, block_n, p, &tmap_c, stage_buf, buf,
+      const int chunks = it.last() ? main_chunks_of_last_unit(block_n) : (block_n >> 5);
+      gemm_epilogue_tile<PAIR, EPI>(t_row, row0, n_idx * block_n, p.N, 0, chunks, p, &tmap_c, stage_buf, buf,
                                     &tempty_bar[acc], lane);
+#ifdef LYCO_GEMM_TRACE
+      if (ew == 0 && lane == 0 && trace_tile < 16) LYCO_TRACE(9 + 2 * trace_tile, clock64());
+      ++trace_tile;
+#endif
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
     if (epi_uses_tma(EPI) && lane == 0) ptx::tma_store_wait_read<0>();  // staging smem must outlive the stores
+#ifdef LYCO_GEMM_TRACE
+    if (ew == 0 && lane == 0) LYCO_TRACE(42, static_cast<unsigned long long>(trace_tile));
+#endif
+  }
+
+  if (warp < 4) {
+    __syncwarp();
+    const int total = p.m_tiles * p.n_tiles * p.splits;
+    if (worker < total) {
+      const int u = (total - worker + workers - 1) / workers - 1;  // this worker's last unit
+      const int tile = (worker + u * workers) / p.splits;
+      const int n_idx = tile % p.n_tiles, m_idx = tile / p.n_tiles;
+      const int row0 = m_idx * rows_per_tile + static_cast<int>(rank) * GEMM_BLOCK_M + warp * 32;
+      gemm_last_unit_helper<PAIR, EPI>(tmem_base, u & 1, row0, n_idx * block_n, p.N, block_n, p, &tmap_c, smem, tlast_bar,
+                                       warp, lane);
+    }
   }
 
   gemm_teardown<PAIR>(tmem_base, warp);
+#ifdef LYCO_GEMM_TRACE
+  if (threadIdx.x == 0) {
+    LYCO_TRACE(40, clock64());
+    LYCO_TRACE(41, trace_globaltimer());
+  }
+#endif
 }
 
 }  // namespace lyco

@@ -9,6 +9,7 @@
 #include <cuda_fp16.h>
 
 #include <cstdint>
+#include "pdl.cuh"
 
 namespace lyco {
 
@@ -28,6 +29,7 @@ __device__ __forceinline__ uint16_t to16<uint16_t>(uint16_t v, int) { return v; 
 template <typename SRC>
 __global__ void __launch_bounds__(256)
 transpose_cast_kernel(const SRC* __restrict__ src, uint16_t* __restrict__ dst, int rows, int cols, int fmt) {
+  pdl_trigger();  // a tensor-core kernel behind this one may start its prologue (pdl.cuh)
   __shared__ uint16_t tile[TR_TILE][TR_TILE + 2];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int c0 = blockIdx.x * TR_TILE, r0 = blockIdx.y * TR_TILE;
@@ -129,6 +131,7 @@ constexpr int FR_MAX_T = 25;     // up to 5x5 filters
 template <typename T, bool BACK>
 __global__ void __launch_bounds__(256) filter_row_relayout_kernel(const T* __restrict__ in, T* __restrict__ out,
                                                                    int C, int taps) {
+  pdl_trigger();  // a tensor-core kernel behind this one may start its prologue (pdl.cuh)
   constexpr int V = 16 / sizeof(T);
   extern __shared__ uint4 fr_smem4[];
   T* tile = reinterpret_cast<T*>(fr_smem4);  // [cn][taps]
@@ -167,6 +170,7 @@ __global__ void __launch_bounds__(256) filter_row_relayout_kernel(const T* __res
 __global__ void __launch_bounds__(256) filter_dgrad_relayout_kernel(const uint16_t* __restrict__ in,
                                                                      uint16_t* __restrict__ out, int O, int C,
                                                                      int taps) {
+  pdl_trigger();  // a tensor-core kernel behind this one may start its prologue (pdl.cuh)
   extern __shared__ uint4 fr_smem4[];
   uint16_t* tile = reinterpret_cast<uint16_t*>(fr_smem4);
   const int o0 = blockIdx.y * 32, c0 = blockIdx.x * 32;

@@ -20,6 +20,7 @@
 #include <stdint.h>
 
 #include "weight_kernels.cuh"
+#include "pdl.cuh"
 
 namespace lyco {
 
@@ -65,6 +66,7 @@ __global__ void __launch_bounds__(256) lokr_mix_kernel(const uint16_t* __restric
                                                        const void* __restrict__ w, int w_dtype, int ldw, int trans,
                                                        int64_t M, int na, int nb, int nc8, int fmt,
                                                        float* __restrict__ zero_buf, int64_t zero_n) {
+  pdl_trigger();  // a tensor-core kernel behind this one may start its prologue (pdl.cuh)
   __shared__ float sw[LK_MAX_G * LK_MAX_G];
   // optional side job: zero-fill the (small) fp32 gradient buffers the NEXT kernels reduce into with atomics — this
   // kernel precedes them on the stream, so the two memset nodes per layer-step disappear from the captured graph

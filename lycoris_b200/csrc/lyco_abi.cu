@@ -163,6 +163,25 @@ int make_tmap_c(CUtensorMap* m, const void* base, uint64_t N, uint64_t M, uint64
   return 0;
 }
 
+// fp32 C tensor map (TMA store / TMA reduce-add epilogue): boxes of 32 rows x 16 columns = 64-byte rows, 64B swizzle
+int make_tmap_c_f32(CUtensorMap* m, const void* base, uint64_t N, uint64_t M, uint64_t ld_elems) {
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return fail("cuTensorMapEncodeTiled is not available from the driver");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld_elems & 3))
+    return fail("fp32 output needs a 16-byte aligned base and a row pitch that is a multiple of 4 elements");
+  cuuint64_t gdim[2] = {N, M};
+  cuuint64_t gstr[1] = {ld_elems * 4};
+  cuuint32_t box[2] = {16, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail("cuTensorMapEncodeTiled (C, fp32) failed (%d): base=%p N=%llu M=%llu ld=%llu", static_cast<int>(r), base,
+                (unsigned long long)N, (unsigned long long)M, (unsigned long long)ld_elems);
+  return 0;
+}
+
 // C tensor map for the NCHW epilogue of the convolution: (pixel, channel, image), boxes of 32 pixels x 32 channels
 int make_tmap_c_nchw(CUtensorMap* m, const void* base, uint64_t PQ, uint64_t O, uint64_t Nb) {
   EncodeTiledFn enc = encode_tiled();
@@ -180,6 +199,26 @@ int make_tmap_c_nchw(CUtensorMap* m, const void* base, uint64_t PQ, uint64_t O, 
   return 0;
 }
 
+inline bool pdl_enabled() {
+  static const bool on = []() { const char* e = getenv("LYCO_PDL"); return !(e && *e == '0'); }();
+  return on;
+}
+
+// cluster shape + programmatic dependent launch (csrc/pdl.cuh) for the tensor-core kernels
+inline void persistent_attrs(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, bool pair) {
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = pair ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg->attrs = attr;
+  cfg->numAttrs = 1;
+  if (pdl_enabled()) {
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg->numAttrs = 2;
+  }
+}
+
 template <typename Kern, typename Params>
 int launch_persistent(Kern kern, bool pair, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
                       const Params& p, int grid, cudaStream_t stream) {
@@ -188,13 +227,8 @@ int launch_persistent(Kern kern, bool pair, const CUtensorMap& ta, const CUtenso
   cfg.blockDim = dim3(lyco::GEMM_THREADS);
   cfg.dynamicSmemBytes = lyco::GEMM_SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = pair ? 2 : 1;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cudaLaunchAttribute attr[2];
+  persistent_attrs(&cfg, attr, pair);
   LYCO_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, p));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
@@ -228,13 +262,8 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
   cfg.blockDim = dim3(lyco::GEMM_THREADS);
   cfg.dynamicSmemBytes = lyco::GEMM_SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cudaLaunchAttribute attr[2];
+  persistent_attrs(&cfg, attr, PAIR);
   LYCO_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, side.ta2 ? *side.ta2 : ta, side.tb2 ? *side.tb2 : tb, p));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
@@ -282,17 +311,26 @@ inline bool conv_pair_enabled() {
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
-// Relative cost of one k-block of a tile.  Tensor-pipe time ~ bn for both variants (a CTA pair runs a
-// 256-row tile at twice the rate); the L2 -> SM feed per CTA is ~(128 + bn) rows for a single CTA and
-// ~(128 + bn/2) for a pair member.  0.85 = measured feed/MMA balance of the 1-CTA kernel at 128x256.
+#ifdef LYCO_GEMM_TRACE
+unsigned long long* g_trace = nullptr;
+#endif
+
+// Relative time of one k-block (4 x tcgen05.mma K = 16) of a tile, per worker.  Measured with tools/gemm_trace.py
+// (8192 x 1280 x 1280, tile widths forced): a CTA pair spends 6.58 / 6.61 / 6.70 / 6.72 / 6.85 us on a 20-k-block tile
+// at bn = 128 / 160 / 192 / 224 / 256 — the instruction time is nearly FLAT in N (the A operand, 128 rows per CTA, is
+// re-read from shared memory for every instruction whatever N is), so a narrower tile buys no time, only more tiles.
+// (Round 1 modelled the cost as proportional to bn and picked 224-wide tiles where 256 needs a wave less.)
+// A single CTA stages all of B itself: L2 -> SM feed ~(128 + bn) rows per k-block, measured 27 % over the pair at
+// 128 x 256.
 struct TileChoice {
   bool pair;
   int bn;
 };
 
 inline double tile_cost(bool pair, int bn) {
-  const double mma = bn, feed = 0.85 * (128 + (pair ? bn / 2 : bn));
-  return (mma > feed ? mma : feed) + 12.0;  // + fixed per-tile overhead (pipeline fill, epilogue hand-off)
+  const double mma = 1.0 + 0.05 * (bn - 128) / 128.0;
+  const double feed = pair ? 0.0 : 0.0033 * (128 + bn);
+  return (mma > feed ? mma : feed) + 0.05;  // + fixed per-tile overhead (pipeline fill, epilogue hand-off)
 }
 
 inline int stages_for(bool pair, int bn) {
@@ -400,6 +438,11 @@ int check_desc(const lyco_delta_desc_t* d, bool allow_f32_weight = false) {
 
 extern "C" {
 
+#ifdef LYCO_GEMM_TRACE
+// debug build only (tools/gemm_trace.py): device buffer of 64 x u64 per CTA that the next lyco_gemm launches fill
+void lyco_debug_set_trace(void* buf) { g_trace = static_cast<unsigned long long*>(buf); }
+#endif
+
 int lyco_abi_version(void) { return LYCO_ABI_VERSION; }
 const char* lyco_last_error(void) { return g_err; }
 uint64_t lyco_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
@@ -474,11 +517,15 @@ int lyco_gemm(const void* A, int a_mn_major, int64_t lda, const void* B, int b_m
   if (!b_mn) { if (make_tmap(&tb, B, K, N, ldb, 64, tc.pair ? bn / 2 : bn)) return 1; }
   else       { if (make_tmap(&tb, B, N, K, ldb, 64, 64)) return 1; }
   if (c_dtype != LYCO_F32) { if (make_tmap_c(&tcm, C, N, M, ldc)) return 1; }
+  else if (make_tmap_c_f32(&tcm, C, N, M, ldc)) return 1;
 
   lyco::GemmParams p;
   p.C = C; p.bias = bias; p.ldc = ldc; p.M = M; p.N = N; p.K = K;
   p.m_tiles = m_tiles; p.n_tiles = n_tiles; p.splits = splits; p.k_blocks = k_blocks; p.k_blocks1 = k_blocks;
   p.block_n = bn; p.stages = stages_for(tc.pair, bn);
+#ifdef LYCO_GEMM_TRACE
+  p.trace = g_trace;
+#endif
   p.fmt = (ab_dtype == LYCO_BF16) ? 1 : 0;
   p.bias_dtype = bias_dtype;
   p.epi_pq = 0;
@@ -531,6 +578,9 @@ int lyco_gemm_dual(const void* A, int64_t lda, const void* B, int b_mn_major, in
   p.C = C; p.bias = bias; p.ldc = ldc; p.M = M; p.N = N; p.K = K + K2;
   p.m_tiles = m_tiles; p.n_tiles = n_tiles; p.splits = 1; p.k_blocks = kb1 + kb2; p.k_blocks1 = kb1;
   p.block_n = bn; p.stages = stages_for(tc.pair, bn);
+#ifdef LYCO_GEMM_TRACE
+  p.trace = nullptr;
+#endif
   p.fmt = (dtype == LYCO_BF16) ? 1 : 0;
   p.bias_dtype = bias_dtype;
   p.epi_pq = 0;
@@ -599,6 +649,9 @@ int lyco_conv2d_fprop(const void* X, const void* Wk, void* Y, const void* bias, 
   cp.g.m_tiles = cdiv(M, pair ? 256 : 128); cp.g.n_tiles = cdiv(O, bn); cp.g.splits = 1;
   cp.g.k_blocks = R * S * (C / 64); cp.g.k_blocks1 = cp.g.k_blocks;
   cp.g.block_n = bn; cp.g.stages = stages_for(pair, bn);
+#ifdef LYCO_GEMM_TRACE
+  cp.g.trace = nullptr;
+#endif
   cp.g.fmt = (dtype == LYCO_BF16) ? 1 : 0; cp.g.bias_dtype = bias_dtype;
   cp.PQ = P * Q; cp.Q = Q; cp.C = C; cp.CB = C / 64; cp.S = S; cp.stride = stride;
   cp.low_w = -pad_w; cp.low_h = -pad_h; cp.tiles_per_tap = 1;
@@ -716,10 +769,14 @@ int lyco_conv2d_wgrad(const void* X, const void* dY, float* dW, int Nb, int H, i
   if (make_tmap_im2col(&tb, X, Nb, H, W, C, R, S, pad_h, pad_w, stride, 64)) return 1;
   lyco::ConvParams cp;
   const int ldw = taps * C;
+  if (make_tmap_c_f32(&tcm, dW, ldw, O, ldw)) return 1;
   cp.g.C = dW; cp.g.bias = nullptr; cp.g.ldc = ldw; cp.g.M = O; cp.g.N = ldw; cp.g.K = Mpix;
   cp.g.m_tiles = m_tiles; cp.g.n_tiles = taps * tiles_per_tap; cp.g.splits = splits; cp.g.k_blocks = k_blocks;
   cp.g.k_blocks1 = k_blocks;
   cp.g.block_n = bn; cp.g.stages = stages_for(pair, bn);
+#ifdef LYCO_GEMM_TRACE
+  cp.g.trace = nullptr;
+#endif
   cp.g.fmt = (dtype == LYCO_BF16) ? 1 : 0; cp.g.bias_dtype = 0;
   cp.PQ = P * Q; cp.Q = Q; cp.C = C; cp.CB = C / 64; cp.S = S; cp.stride = stride;
   cp.low_w = -pad_w; cp.low_h = -pad_h; cp.tiles_per_tap = tiles_per_tap;

@@ -67,6 +67,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 }
+// Whole-warp wait for an event that is a long way off (the helpers of the last drain park here for most of the
+// kernel): one lane polls with a sleep between tries, so the warp stays out of the issue slots of the epilogue warp it
+// shares a scheduler with; every lane then observes the completed phase itself.
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity, int lane) {
+  if (lane == 0 && !mbar_try_wait(bar, parity)) {
+    uint64_t t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (!mbar_try_wait(bar, parity)) {
+      __nanosleep(100);
+      uint64_t t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 4000000000ull) {
+        printf("lyco: mbarrier timeout (parked) blk=%d thr=%d\n", blockIdx.x, threadIdx.x);
+        __trap();
+      }
+    }
+  }
+  __syncwarp();
+  mbar_wait(bar, parity);
+}
 
 // --------------------------------------------------------------------- TMA --
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
@@ -93,6 +113,14 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int32_t c0,
                                              int32_t c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+// shared -> global with the reduction done by the TMA unit: global[box] += smem[box] (element type from the tensor map;
+// whole 32-byte sectors per request instead of one 16-byte red per lane and row)
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* smem_src, int32_t c0, int32_t c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(m)),
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");

@@ -8,6 +8,7 @@
 #include <stdint.h>
 
 #include "../../include/lyco_b200.h"
+#include "pdl.cuh"
 
 namespace lyco {
 
@@ -130,6 +131,7 @@ __device__ __forceinline__ void lr_product(float (&acc)[4][8], const void* a, co
 template <bool LOHA>
 __global__ void __launch_bounds__(256) merge_lowrank_kernel(lyco_delta_desc_t d, const uint16_t* __restrict__ W,
                                                             uint16_t* __restrict__ Wout) {
+  pdl_trigger();  // a tensor-core kernel behind this one may start its prologue (pdl.cuh)
   __shared__ __align__(16) float sa[LR_ROWS][LR_RC];
   __shared__ __align__(16) float sb[LR_RC][LR_COLS];
   const int N = d.out_dim, K = d.in_dim, r = d.rank;
@@ -187,6 +189,7 @@ constexpr int PD_NONE = -1;
 template <int VEC, int FD = DT_RUNTIME, int WD = DT_RUNTIME, int PD = PD_RUNTIME>
 __global__ void __launch_bounds__(256) merge_lokr_kernel(lyco_delta_desc_t d, const uint16_t* __restrict__ W,
                                                          uint16_t* __restrict__ Wout) {
+  pdl_trigger();  // a tensor-core kernel behind this one may start its prologue (pdl.cuh)
   const int f_dtype = FD == DT_RUNTIME ? d.f_dtype : FD;
   const int w_dtype = WD == DT_RUNTIME ? d.w_dtype : WD;
   const int pre_round = PD == PD_RUNTIME ? d.pre_round : (PD == PD_NONE ? 0 : 1);
@@ -230,6 +233,7 @@ __global__ void __launch_bounds__(256) merge_lokr_kernel(lyco_delta_desc_t d, co
 template <int FD, int WD, int PD>
 __global__ void __launch_bounds__(256) merge_lokr_rows_kernel(lyco_delta_desc_t d, const uint16_t* __restrict__ W,
                                                               uint16_t* __restrict__ Wout) {
+  pdl_trigger();  // a tensor-core kernel behind this one may start its prologue (pdl.cuh)
   constexpr int f_dtype = FD, w_dtype = WD;
   constexpr int pre_round = PD == PD_NONE ? 0 : 1;
   constexpr int pre_dtype = PD == PD_NONE ? LYCO_F32 : PD;
@@ -294,6 +298,7 @@ __global__ void __launch_bounds__(256) merge_lokr_rows_kernel(lyco_delta_desc_t 
 template <int D16 = DT_RUNTIME>
 __global__ void __launch_bounds__(256) merge_raw_kernel(lyco_delta_desc_t d, const uint16_t* __restrict__ W,
                                                         uint16_t* __restrict__ Wout) {
+  pdl_trigger();  // a tensor-core kernel behind this one may start its prologue (pdl.cuh)
   const int w_dtype = D16 == DT_RUNTIME ? d.w_dtype : D16;
   const int pre_round = D16 == DT_RUNTIME ? d.pre_round : 1;
   const int pre_dtype = D16 == DT_RUNTIME ? d.pre_dtype : D16;
@@ -326,6 +331,7 @@ __global__ void __launch_bounds__(256) merge_raw_kernel(lyco_delta_desc_t d, con
 // G = rnd16(gscale * dW [* P]) — operand of the skinny tensor-core gradient contractions
 __global__ void __launch_bounds__(256) grad_prep_kernel(const float* __restrict__ dW, const uint16_t* __restrict__ P,
                                                         uint16_t* __restrict__ G, int64_t n8, float gscale, int dtype) {
+  pdl_trigger();  // a tensor-core kernel behind this one may start its prologue (pdl.cuh)
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const float4 a = __ldg(reinterpret_cast<const float4*>(dW) + 2 * i);
@@ -349,6 +355,7 @@ __global__ void __launch_bounds__(256) grad_prep_kernel(const float* __restrict_
 // (IA)^3: W' = W * (1 + w*mult) on output rows or input channels (ia3.py:91-102)
 __global__ void __launch_bounds__(256) merge_ia3_kernel(lyco_delta_desc_t d, const uint16_t* __restrict__ W,
                                                         uint16_t* __restrict__ Wout) {
+  pdl_trigger();  // a tensor-core kernel behind this one may start its prologue (pdl.cuh)
   const int K = d.in_dim;
   const int64_t total = static_cast<int64_t>(d.out_dim) * K;
   const int cd = (d.f_dtype == LYCO_F32) ? LYCO_F32 : d.f_dtype;  // dtype the scale is computed in

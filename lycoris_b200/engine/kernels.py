@@ -52,10 +52,34 @@ def gemm_supported(*mats) -> bool:
 _gemm_profile = None  # bench.py: list collecting (start_event, end_event, flops, M, N, K, bytes) per launch
 
 
-def set_gemm_profiler(sink):
-    """Record a CUDA-event pair around every GEMM launch into ``sink`` (None disables)."""
-    global _gemm_profile
+_gemm_profile_refill = (0, 0)  # (every n profiled launches, spin this many GPU cycles first)
+_gemm_profile_calls = 0
+
+
+def set_gemm_profiler(sink, refill_every=0, refill_cycles=0):
+    """Record a CUDA-event pair around every GEMM launch into ``sink`` (None disables).
+
+    ``refill_every`` / ``refill_cycles``: before every n-th bracketed launch the stream first spins for that many GPU
+    cycles (outside the bracket).  The host gets ahead of the GPU again during the spin, so the event pair brackets the
+    kernel on a busy stream and not the GPU waiting for Python to reach the launch (an eager step that is host-bound
+    on a slow box would otherwise count host time as kernel time)."""
+    global _gemm_profile, _gemm_profile_refill, _gemm_profile_calls
     _gemm_profile = sink
+    _gemm_profile_refill = (int(refill_every), int(refill_cycles))
+    _gemm_profile_calls = 0
+
+
+def _bracket_open():
+    global _gemm_profile_calls
+    every, cycles = _gemm_profile_refill
+    if every > 0:
+        if _gemm_profile_calls % every == 0:
+            torch.cuda._sleep(cycles)
+        _gemm_profile_calls += 1
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    return e0, e1
 
 
 def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, out_dtype=None, split_k=0, out=None, accumulate=False):
@@ -83,9 +107,7 @@ def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, out_dtype=None, split_k=0, 
         out = torch.empty((M, N), device=a.device, dtype=out_dtype)
     prof = _gemm_profile
     if prof is not None:
-        e0 = torch.cuda.Event(enable_timing=True)
-        e1 = torch.cuda.Event(enable_timing=True)
-        e0.record()
+        e0, e1 = _bracket_open()
     rc = lib.lyco_gemm(
         _ptr(a), int(a_mn), a.stride(0),
         _ptr(b), int(b_mn), b.stride(0),
@@ -116,9 +138,7 @@ def gemm_dual(a, b, a2, b2, *, b_mn=False, bias=None):
     out = torch.empty((M, N), device=a.device, dtype=a.dtype)
     prof = _gemm_profile
     if prof is not None:
-        e0 = torch.cuda.Event(enable_timing=True)
-        e1 = torch.cuda.Event(enable_timing=True)
-        e0.record()
+        e0, e1 = _bracket_open()
     rc = _lib.load().lyco_gemm_dual(
         _ptr(a), a.stride(0), _ptr(b), int(b_mn), b.stride(0), Kd,
         _ptr(a2), a2.stride(0), _ptr(b2), b2.stride(0), K2,
