@@ -436,11 +436,20 @@ def run_engine(args):
         step = step_nc  # the instrumented eager steps below run without the collective (rank-local)
 
     # instrumented eager steps: CUDA-event pair around every lyco_gemm launch (same stream)
+    # Pass 1 (no brackets kept): how long the HOST needs for one eager step.  Pass 2: before every 8th bracket the
+    # stream first spins (outside the brackets) for 1.5x the host time of 8 GEMM calls and everything between them, so
+    # the host is ahead of the GPU at every bracket and the event pairs hold kernel time, not the GPU waiting for the
+    # eager Python launch path (on a slow or busy host the brackets otherwise count host time: 136 ms instead of 95).
+    K.set_gemm_profiler([])
+    t_host0 = time.perf_counter()
+    step()
+    host_s = time.perf_counter() - t_host0
+    torch.cuda.synchronize()
+    n_brackets = max(1, len(K._gemm_profile))
+    refill_every = 8
+    refill_s = min(0.025, 1.5 * refill_every * host_s / n_brackets)
     sink = []
-    # keep the GPU busy for ~0.6 s first so the host runs ahead of it, and again for 4 ms before every 32nd bracket
-    # (outside the brackets): the event pairs then bracket kernel execution on a busy stream, not the GPU waiting for
-    # the (slower) eager Python launch path — on a host-bound box the brackets otherwise count host time
-    K.set_gemm_profiler(sink, refill_every=32, refill_cycles=int(4e-3 * 1.9e9))
+    K.set_gemm_profiler(sink, refill_every=refill_every, refill_cycles=int(refill_s * 1.9e9))
     l0 = _lib.launch_count()
     torch.cuda._sleep(int(0.6 * 1.9e9))
     step()
@@ -559,6 +568,8 @@ def run_engine(args):
             # all event brackets (tensor-bound + HBM-bound launches) over the CUPTI kernel time of the same launches:
             # ~1.1 when the brackets hold kernels only, well above when the eager step was host-bound
             "event_ms_over_cupti_ms": ((gemm_ms + skinny_ms) / gemm_kernel_ms) if gemm_kernel_ms else None,
+            # host time of one eager step and the spin placed in front of every 8th bracket so that the host stays ahead
+            "host_eager_step_ms": host_s * 1e3, "bracket_refill_ms": refill_s * 1e3,
             # (CUPTI totals cannot be split by shape: ALL gemm_sm100_kernel launches, tensor-bound and HBM-bound alike)
             "achieved_cupti_all_gemm_launches": ((gemm_flops + skinny_flops) / (gemm_kernel_ms * 1e-3) / 1e12) if gemm_kernel_ms else None,
             # ALGORITHMIC work of the adapter path (c*F1 + F_side, c = 2 or 3 — never the

@@ -55,6 +55,17 @@ def main():
         k.conv2d_fprop(dy, wd, None, 3, 3, (1, 1), 1)
         k.conv2d_wgrad(x, dy, 3, 3, (1, 1), 1)
     torch.cuda.synchronize()
+    # LoHa tile kernel (lyco_hada): forward merge and the gradient operands, rank 32, on a small and a large layer
+    for (N, Kd) in ((1280, 1280), (10240, 1280)):
+        r = 32
+        f = [(torch.randn(N, r, device="cuda") * 0.1).to(torch.bfloat16), (torch.randn(r, Kd, device="cuda") * 0.1).to(torch.bfloat16),
+             (torch.randn(N, r, device="cuda") * 0.1).to(torch.bfloat16), (torch.randn(r, Kd, device="cuda") * 0.1).to(torch.bfloat16)]
+        W = (torch.randn(N, Kd, device="cuda") * 0.03).to(torch.bfloat16)
+        dW = torch.randn(N, Kd, device="cuda")
+        for _ in range(reps):
+            k.hada_merge(f, W, 1.0, 1.0, 1.0)
+            k.hada_grad_operands(f, dW, 1.0)
+    torch.cuda.synchronize()
     print("ncu target done")
 
 

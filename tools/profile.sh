@@ -12,7 +12,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none --nvtx --nvtx-include 
 python tools/ncu_launch_list_summary.py gpurun_out/launches_step.csv > gpurun_out/launch_list_step_summary.txt 2>&1
 gzip -f gpurun_out/launches_step.csv
 REPS=1 ncu --set full --clock-control none --import-source on \
-    -k regex:"gemm_sm100_kernel|conv_sm100_kernel|merge_lokr|grad_lokr|lokr_mix|lokr_w1grad" -c 36 \
+    -k regex:"gemm_sm100_kernel|conv_sm100_kernel|hada_sm100_kernel|merge_lokr|grad_lokr|lokr_mix|lokr_w1grad" -c 40 \
     -o gpurun_out/prof_r02 python tools/ncu_target.py > gpurun_out/ncu_full.log 2>&1
 ncu -i gpurun_out/prof_r02.ncu-rep --page raw --csv > gpurun_out/prof_r02_raw.csv 2>/dev/null
 python tools/ncu_summarize.py < gpurun_out/prof_r02_raw.csv > gpurun_out/ncu_full_summary.txt 2>&1
