@@ -241,13 +241,6 @@ def _lowrank_tc_dtype(spec, factors, out_dim, in_dim, ac_dtype):
 def _lowrank_operands(spec, factors, prod):
     """16-bit copies of the factors as the matmul sees them (DyLoRA folds alpha/(b+1)*mult into `down`
     in the parameter dtype first, dylora.py:117)."""
-    if (len(factors) > 1 and not torch.is_grad_enabled() and all(f.dtype != prod and f.is_contiguous() for f in factors)
-            and not (spec.algo == K.ALGO_DYLORA and spec.m_in != 1.0)):
-        # one multi-tensor cast instead of one launch per factor (LoHa: 4 per layer-step, 3152 launches / 6 ms of the
-        # SDXL cfg #3 step); same round-to-nearest-even as Tensor.to
-        ops = [torch.empty_like(f, dtype=prod) for f in factors]
-        torch._foreach_copy_(ops, list(factors))
-        return ops
     ops = [f.to(prod) for f in factors]
     if spec.algo == K.ALGO_DYLORA and spec.m_in != 1.0:
         ops[1] = (factors[1] * spec.m_in).to(prod)
