@@ -71,12 +71,12 @@ uint64_t lyco_launch_count(void);
  *   likewise b_mn_major for B ([N, K] or [K, N]).
  *   lda / ldb: leading dimension (elements) of the array as stored.
  *   c_dtype: LYCO_BF16 / LYCO_F16 (store, optional bias[N]) or LYCO_F32
- *            (store; with split_k > 1 partials are reduced with fp32 atomics
- *             into C, which the call zero-fills first).
+ *            (store; with split_k > 1 the partials are added into C — fp32 reductions
+ *             performed by the TMA unit, in no fixed order — which the call zero-fills first).
  *   ab_dtype: LYCO_BF16 or LYCO_F16.
  *   bias / bias_dtype: optional [N] vector added in the epilogue (NULL = none).
  *   split_k: 0 = choose automatically; otherwise number of reduction splits.
- *   accumulate: fp32 C only — C += A·Bᵀ (fp32 atomics, no zero fill).  Lets fp32 layers be contracted
+ *   accumulate: fp32 C only — C += A·Bᵀ (fp32 reductions as above, no zero fill).  Lets fp32 layers be contracted
  *            as three bf16 products (hi·hi + hi·lo + lo·hi) into one fp32 accumulator.
  *
  * Replaces, per wrapped layer and step, the ATen library calls at
@@ -159,7 +159,7 @@ int lyco_transpose_cast(const void* src, void* dst, int batch, int rows, int col
 
 /*
  * dW[o, r, s, c] (fp32, [O, R*S*C]) = sum_{n,p,q} dY[n,p,q,o] * X[n, p*stride - pad_h + r, q*stride - pad_w + s, c]
- * dY is NHWC [Nb, P, Q, O].  Needs C % 64 == 0, O % 8 == 0.  split_k as in lyco_gemm.
+ * dY is NHWC [Nb, P, Q, O].  Needs C % 64 == 0, O % 8 == 0, dW 16-byte aligned.  split_k as in lyco_gemm.
  * Replaces autograd's weight-gradient of the delta convolution (d(delta_weight), locon.py:331).
  */
 int lyco_conv2d_wgrad(const void* X, const void* dY, float* dW, int Nb, int H, int W, int C, int O,
