@@ -20,25 +20,10 @@ class IA3Module(LycorisBaseModule):
     weight_list = ["weight", "on_input"]
     weight_list_det = ["on_input"]
 
-    def __init__(
-        self,
-        lora_name,
-        org_module: nn.Module,
-        multiplier=1.0,
-        lora_dim=4,
-        alpha=1,
-        dropout=0.0,
-        rank_dropout=0.0,
-        module_dropout=0.0,
-        use_tucker=False,
-        use_scalar=False,
-        rank_dropout_scale=False,
-        weight_decompose=False,
-        bypass_mode=None,
-        rs_lora=False,
-        train_on_input=False,
-        **kwargs,
-    ):
+    # positional contract of every adapter constructor (wrapper.py / kohya.py call it positionally)
+    def __init__(self, lora_name, org_module: nn.Module, multiplier=1.0, lora_dim=4, alpha=1, dropout=0.0,
+                 rank_dropout=0.0, module_dropout=0.0, use_tucker=False, use_scalar=False, rank_dropout_scale=False,
+                 weight_decompose=False, bypass_mode=None, rs_lora=False, train_on_input=False, **kwargs):
         """if alpha == 0 or None, alpha is rank (no scaling)."""
         super().__init__(
             lora_name, org_module, multiplier, dropout, rank_dropout, module_dropout, rank_dropout_scale, bypass_mode
